@@ -1,0 +1,117 @@
+/* drb200.h — C ABI of libdrb200.so, the B200 (sm_100a) implementation of the DiffusionRenderer denoising hot path.
+ *
+ * The reference (eggsbenedicto/DiffusionRenderer-ComfyUI) has no FFI of its own: its hot path is Python calling
+ * PyTorch library ops.  Each entry point below therefore names the reference Python call site(s) it replaces
+ * (file:line into the reference tree).  INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; bf16 tensors are row-major, 16-byte aligned;
+ *   - `stream` is the caller's cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream);
+ *     calls only enqueue work on it and never synchronise the device;
+ *   - return value: 0 = OK, negative = DRB_ERR_*; drb_last_error() returns a thread-local message;
+ *   - nothing is retained past a call (no hidden allocations, no global state besides a tensor-map entry point
+ *     and the SM count cache); scratch buffers are provided by the caller.
+ */
+#ifndef DRB200_H_
+#define DRB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRB_OK 0
+#define DRB_ERR_INVALID (-1)   /* bad shape / alignment / argument   -> Python ValueError */
+#define DRB_ERR_CUDA (-2)      /* a CUDA runtime / driver call failed -> Python RuntimeError */
+#define DRB_ERR_UNSUPPORTED (-3)
+
+/* Epilogue selectors for drb_gemm_bf16 */
+#define DRB_EPI_STORE 0          /* out = bf16(acc)                                        nn.Linear, bias=False            */
+#define DRB_EPI_GELU 1           /* out = bf16(gelu_erf(bf16(acc)))                        CleanGeneralDIT.py:454-457       */
+#define DRB_EPI_GATED_RESIDUAL 2 /* out = bf16(resid + bf16(gate[n] * bf16(acc)))          CleanGeneralDIT.py:517           */
+
+const char* drb_last_error(void);
+int drb_version(void);
+/* 1 when the current device is compute capability 10.x (the only target), else 0. */
+int drb_device_supported(void);
+
+/* ---- dense projections --------------------------------------------------------------------------------------
+ * out[M,N] = epilogue( A[M,K] @ W[N,K]^T ), bf16 in / fp32 accumulate in TMEM / bf16 out (tcgen05 + TMA).
+ * Replaces every nn.Linear on the token stream: to_q/to_k/to_v (CleanGeneralDIT.py:273-276, fused as one
+ * [3D,D] weight), to_out (:304), layer1/layer2 (:454,:460), x_embedder.proj['1'] (:417), final_layer.linear (:590).
+ * lda/ldw/ldo/ldr are row pitches in elements (multiples of 8).  `resid`/`gate` only for DRB_EPI_GATED_RESIDUAL
+ * (`out` may alias `resid`).  cta_group: 1 = one CTA per 128x256 tile, 2 = CTA pair per 256x256 tile, 0 = auto. */
+int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                  int M, int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
+                  int cta_group, void* stream);
+
+/* ---- self-attention ------------------------------------------------------------------------------------------
+ * o[s, h*128 + d] = softmax_j(q[s,h,:]·k[j,h,:] / sqrt(128)) v[j,h,d]; no mask, no dropout, head_dim 128.
+ * Replaces PytorchDotProductAttention.forward / F.scaled_dot_product_attention (CleanGeneralDIT.py:181-203), with
+ * the head-flattened (S, H*128) output the reference's to_out expects (SURVEY.md defect D1).
+ * q,k,v: row s at q + s*ld_qkv elements, head h at column h*128 (e.g. three column blocks of one [S,3D] buffer).
+ * `kv_len` keys/values, `q_len` queries (equal for the single-GPU path; they differ under context parallelism). */
+int drb_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                       int q_len, int kv_len, int num_heads, void* stream);
+
+/* ---- fused elementwise family ----------------------------------------------------------------------------------
+ * AdaLN: out = bf16(bf16(bf16(LN(x)) * bf16(1+scale)) + shift), LN over `D` without affine, eps 1e-6, fp32 stats
+ * (CleanGeneralDIT.py:7-11,:481,:506).  If `add_vec` != NULL the residual stream is first updated in place,
+ * x <- bf16(x + bf16(add_gate * add_vec)), which is the whole degenerate cross-attention sub-block (:512-517 with a
+ * one-token context). */
+int drb_adaln_modulate(void* x, void* out, const void* shift, const void* scale, const void* add_gate,
+                       const void* add_vec, int rows, int D, void* stream);
+
+/* q,k <- RoPE(RMSNorm_head(q,k)) in place on the [S, 3D] projection buffer (v untouched).
+ * Per head of 128: bf16(rmsnorm_fp32(x) * w) (CleanGeneralDIT.py:23-33,:288-289) then
+ * bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)) with cos/sin = bf16(cos/sin(angle)) (:67-80).
+ * `cos_tab`,`sin_tab`: bf16 [S,128] tables built by the host from the reference's angle formula (:94-159). */
+int drb_qk_norm_rope(void* qkv, int64_t ld, const void* wq, const void* wk, const void* cos_tab,
+                     const void* sin_tab, int S, int num_heads, void* stream);
+
+/* y[n] = bf16( sum_k W[n,k] * act(x[k]) ) for one bf16 vector x; act: 0 = identity, 1 = SiLU (computed in fp32 on the
+ * bf16 input and rounded to bf16 first, as nn.SiLU on a bf16 tensor does).  `add` (nullable) is added afterwards in
+ * bf16: y = bf16(y + add).  Replaces the B=1 nn.Linear GEMVs of the timestep / AdaLN-LoRA path
+ * (CleanGeneralDIT.py:357-364, :483-488, :500-501, :558-572) and the context projections of cross-attention (:275-276,:304). */
+int drb_gemv_bf16(const void* W, int64_t ldw, const void* x, void* y, const void* add, int N, int K, int act,
+                  void* stream);
+/* Batched form: `count` independent GEMVs sharing x; W_b = W + b*w_batch_stride, y_b = y + b*y_batch_stride,
+ * add_b = add + b*add_batch_stride (elements; add may be NULL; add_batch_stride may be 0 to share). */
+int drb_gemv_bf16_batched(const void* W, int64_t ldw, int64_t w_batch_stride, const void* x, int64_t x_batch_stride,
+                          void* y, int64_t y_batch_stride, const void* add, int64_t add_batch_stride, int count,
+                          int N, int K, int act, void* stream);
+
+/* Timestep embedding: sigma (fp32 scalar on device) -> s~ = bf16(sigma); e = bf16([cos(s~ w_i), sin(s~ w_i)]),
+ * w_i = exp(-ln(1e4) i / (D/2)) (CleanGeneralDIT.py:321-335, :664); emb = bf16(rmsnorm_fp32(e) * w_aff) (:666).
+ * Writes e_out[D] and emb_out[D] (bf16). */
+int drb_sigma_embedding(const float* sigma, const void* w_aff, void* e_out, void* emb_out, int D, void* stream);
+
+/* EDM input scaling + patchify of the noisy latent (model_diffusion_renderer.py:30-44; CleanGeneralDIT.py:409-414):
+ * x_in = bf16(fp32(x_t) / sqrt(sigma^2 + 0.25)) scattered into token rows of `tokens` [S, ld_tok] at feature
+ * c*4 + m*2 + n for channel c in [0,C).  x_t: bf16 [C,T,H,W]. */
+int drb_scale_patchify(const void* x_t, const float* sigma, void* tokens, int64_t ld_tok, int C, int T, int H, int W,
+                       void* stream);
+/* Patchify constant channels (latent condition + ones padding mask, CleanGeneralDIT.py:669-675) once per pass:
+ * src bf16 [C,T,H,W] -> tokens[:, (c0+c)*4 + m*2 + n]; if `ones_channel` >= 0 that channel's 4 features are set to 1,
+ * and features in [zero_from, ld_tok) are zeroed (K padding). */
+int drb_patchify_condition(const void* src, void* tokens, int64_t ld_tok, int c0, int C, int T, int H, int W,
+                           int ones_channel, int zero_from, void* stream);
+
+/* Final unpatchify + Euler update (CleanGeneralDIT.py:709-716; model_diffusion_renderer.py:46-82, :232):
+ * F[c,t,2h+ph,2w+pw] = y[s, (ph*2+pw)*C + c];  optional CFG  F = bf16(Fc + bf16(g * bf16(Fc - Fu)));
+ * den = c_skip x + c_out F;  x_next = bf16(x + (x - den)/sigma * (sigma_next - sigma)), all fp32 inside.
+ * y_cond / y_uncond: bf16 [S, ld_y]; x_t in / x_next out: bf16 [C,T,H,W] (may alias); F_out (nullable): bf16 [C,T,H,W]. */
+int drb_unpatchify_euler(const void* y_cond, const void* y_uncond, int64_t ld_y, float guidance, const float* sigma,
+                         const float* sigma_next, const void* x_t, void* x_next, void* F_out, int C, int T, int H,
+                         int W, void* stream);
+
+/* Decode post-process (diffusion_renderer_pipeline.py:300-318): optional normal re-normalisation blend, then
+ * (1+v).clamp(0,2)/2*255 -> uint8 (truncating), BCTHW -> BTHWC.  video: bf16 [3,T,H,W]; out: uint8 [T,H,W,3]. */
+int drb_postprocess_u8(const void* video, void* out_u8, int T, int H, int W, int normalize_normal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRB200_H_ */
