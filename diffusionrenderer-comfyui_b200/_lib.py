@@ -1,0 +1,68 @@
+"""ctypes binding of libdrb200.so (include/drb200.h).  There is NO fallback: if the library is missing or a call
+fails, a Python exception is raised (ValueError for DRB_ERR_INVALID, RuntimeError otherwise)."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdrb200.so")
+
+DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_UNSUPPORTED = 0, -1, -2, -3
+EPI_STORE, EPI_GELU, EPI_GATED_RESIDUAL = 0, 1, 2
+
+# name -> argtypes, in the order of include/drb200.h (tests check that every one is exported)
+PROTOTYPES = {
+    "drb_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
+                      c_int64, c_void_p, c_int, c_void_p],
+    "drb_attention_bf16": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
+    "drb_adaln_modulate": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "drb_qk_norm_rope": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "drb_gemv_bf16": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "drb_gemv_bf16_batched": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
+                              c_int, c_int, c_int, c_void_p],
+    "drb_sigma_embedding": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "drb_scale_patchify": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p],
+    "drb_patchify_condition": [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "drb_unpatchify_euler": [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int, c_int, c_int, c_int, c_void_p],
+    "drb_postprocess_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen libdrb200.so (built by build.py) and declare every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "The B200 path has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.drb_last_error.restype = c_char_p
+    lib.drb_last_error.argtypes = []
+    lib.drb_version.restype = c_int
+    lib.drb_device_supported.restype = c_int
+    for name, args in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == DRB_OK:
+        return
+    msg = load().drb_last_error().decode(errors="replace")
+    if rc == DRB_ERR_INVALID:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

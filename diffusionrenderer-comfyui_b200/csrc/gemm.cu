@@ -1,0 +1,321 @@
+// drb_gemm_bf16 — out[M,N] = epilogue(A[M,K] @ W[N,K]^T) on tcgen05 tensor cores.
+//
+// Replaces every nn.Linear on the token stream of the reference DiT (CleanGeneralDIT.py:273-276, :304, :454-460,
+// :417, :590).  bf16 operands staged by TMA (128-byte swizzle), fp32 accumulators in TMEM, bf16 output.
+//
+// Structure (persistent, warp-specialised, one CTA — or one CTA pair — per SM):
+//   warp 0      TMA producer            (ring of kStages {A,B} k-blocks of 64)
+//   warp 1      tcgen05.mma issuer      (one thread; leader CTA only in pair mode)
+//   warp 2      TMEM allocator          (512 columns = 2 accumulator stages x 256 fp32 columns)
+//   warps 4..7  epilogue                (tcgen05.ld -> registers -> epilogue math -> 16-byte global stores)
+// kCtaGroup = 1: tile 128 x 256 per CTA.  kCtaGroup = 2: tile 256 x 256 per CTA pair (cta_group::2 MMA, each CTA
+// stages its own 128 rows of A and its own 128-row half of W, halving the shared-memory/L2 operand traffic).
+// The MMA of tile i+1 overlaps the epilogue of tile i through the two TMEM accumulator stages.
+//
+// Roofline: tensor pipe.  Algorithmic work = 2*M*N*K flop per launch.
+#include <math.h>
+
+#include "../../include/drb200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace drb {
+namespace {
+
+constexpr int kBlockM = 128;   // rows of A per CTA
+constexpr int kBlockN = 256;   // columns of the output tile (rows of W)
+constexpr int kBlockK = 64;    // one 128-byte swizzle atom of bf16
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 256;
+constexpr int kBandTilesN = 16;  // rasterisation: bands of 16 n-tiles keep the W band (<= 32 MB at K=4096) in L2
+
+template <int kCtaGroup>
+struct GemmCfg {
+  static constexpr int kBRows = kBlockN / kCtaGroup;                      // W rows staged per CTA
+  static constexpr int kABytes = kBlockM * kBlockK * 2;                   // 16 KB
+  static constexpr int kBBytes = kBRows * kBlockK * 2;                    // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;                   // 48 KB / 32 KB
+  static constexpr int kStages = kCtaGroup == 1 ? 4 : 6;                  // 192 KB of operand ring
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  __nv_bfloat16* out;
+  int64_t ldo;
+  const __nv_bfloat16* resid;
+  int64_t ldr;
+  const __nv_bfloat16* gate;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& m, int& n) {
+  const int per_band = tiles_m * kBandTilesN;
+  const int band = t / per_band;
+  const int r = t - band * per_band;
+  const int n0 = band * kBandTilesN;
+  const int w = min(kBandTilesN, tiles_n - n0);
+  m = r / w;
+  n = n0 + (r - m * w);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int kCtaGroup, int kEpi>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtaGroup == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+
+  const int tile_m_rows = kBlockM * kCtaGroup;
+  const int tiles_m = (p.M + tile_m_rows - 1) / tile_m_rows;
+  const int tiles_n = (p.N + kBlockN - 1) / kBlockN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int cluster_id = blockIdx.x / kCtaGroup;
+  const int num_clusters = gridDim.x / kCtaGroup;
+
+  if (warp_idx == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);   // one arrival per epilogue warp of every CTA in the group
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc<kCtaGroup>(tmem_slot, 512);
+    tmem_relinquish<kCtaGroup>();
+  }
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int tm, tn;
+        tile_coords(t, tiles_m, tiles_n, tm, tn);
+        const int row_a = tm * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
+        const int row_b = tn * kBlockN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if constexpr (kCtaGroup == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, row_a);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, row_b);
+          } else {
+            // both CTAs' bytes are accounted on the leader's barrier
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * 2);
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * kBlockK, row_a);
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * kBlockK, row_b);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kBlockN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = make_desc_kmajor_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_ss<kCtaGroup>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (kCtaGroup == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_pair(&empty_bar[stage], 0x3);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (kCtaGroup == 1) umma_commit(&tmem_full_bar[as]);
+        else umma_commit_pair(&tmem_full_bar[as], 0x3);
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int q = warp_idx - 4;   // == warp_idx % 4: the TMEM lane quadrant this warp may read
+    int iter = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
+      int tm, tn;
+      tile_coords(t, tiles_m, tiles_n, tm, tn);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int row = tm * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;
+      const int col0 = tn * kBlockN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBlockN;
+      const bool row_ok = row < p.M;
+      __nv_bfloat16* out_row = p.out + static_cast<int64_t>(row) * p.ldo;
+      const __nv_bfloat16* res_row = kEpi == DRB_EPI_GATED_RESIDUAL ? p.resid + static_cast<int64_t>(row) * p.ldr : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / 32; ++c) {
+        const int col = col0 + c * 32;
+        if (col >= p.N) break;   // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {   // 4 groups of 8 columns = one 16-byte store each
+          const int cg = col + g * 8;
+          if (!row_ok || cg >= p.N) continue;
+          uint32_t o[4];
+          if constexpr (kEpi == DRB_EPI_STORE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
+          } else if constexpr (kEpi == DRB_EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a0 = bf16_round(__uint_as_float(r[g * 8 + 2 * j]));
+              const float a1 = bf16_round(__uint_as_float(r[g * 8 + 2 * j + 1]));
+              o[j] = pack_bf16x2(gelu_erf(a0), gelu_erf(a1));
+            }
+          } else {
+            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + cg);
+            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.gate + cg));
+            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a0 = bf16_round(__uint_as_float(r[g * 8 + 2 * j]));
+              const float a1 = bf16_round(__uint_as_float(r[g * 8 + 2 * j + 1]));
+              const float t0 = bf16_round(bf16_lo(gg[j]) * a0);
+              const float t1 = bf16_round(bf16_hi(gg[j]) * a1);
+              o[j] = pack_bf16x2(bf16_lo(rr[j]) + t0, bf16_hi(rr[j]) + t1);
+            }
+          }
+          *reinterpret_cast<uint4*>(out_row + cg) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      // release the accumulator stage to the MMA issuer (the leader's barrier)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 1) mbar_arrive(&tmem_empty_bar[as]);
+        else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  __syncwarp();   // reconverge the single-lane roles before the aligned barriers below
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<kCtaGroup>(tmem_base, 512);
+  }
+}
+
+template <int kCtaGroup, int kEpi>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  auto kernel = gemm_bf16_kernel<kCtaGroup, kEpi>;
+  static bool configured = false;   // per template instance
+  if (!configured) {
+    DRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tile_m_rows = kBlockM * kCtaGroup;
+  const int tiles = ((p.M + tile_m_rows - 1) / tile_m_rows) * ((p.N + kBlockN - 1) / kBlockN);
+  int sms = num_sms();
+  int clusters = sms / kCtaGroup;
+  if (clusters > tiles) clusters = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * kCtaGroup);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DRB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
+  return 0;
+}
+
+template <int kCtaGroup>
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case DRB_EPI_STORE: return launch_gemm<kCtaGroup, DRB_EPI_STORE>(ta, tb, p, s);
+    case DRB_EPI_GELU: return launch_gemm<kCtaGroup, DRB_EPI_GELU>(ta, tb, p, s);
+    case DRB_EPI_GATED_RESIDUAL: return launch_gemm<kCtaGroup, DRB_EPI_GATED_RESIDUAL>(ta, tb, p, s);
+    default: return fail("drb_gemm_bf16", "unknown epilogue");
+  }
+}
+
+}  // namespace
+}  // namespace drb
+
+extern "C" int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M,
+                             int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
+                             int cta_group, void* stream) {
+  using namespace drb;
+  DRB_REQUIRE(A && W && out, "null pointer");
+  DRB_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
+  DRB_REQUIRE(N % 8 == 0 && K % 8 == 0, "N and K must be multiples of 8");
+  DRB_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "row pitches must be multiples of 8 elements");
+  DRB_REQUIRE(lda >= K && ldw >= K && ldo >= N, "row pitch smaller than the row");
+  DRB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out not 16-byte aligned");
+  if (epilogue == DRB_EPI_GATED_RESIDUAL) {
+    DRB_REQUIRE(resid && gate, "gated-residual epilogue needs resid and gate");
+    DRB_REQUIRE(ldr % 8 == 0 && ldr >= N, "bad residual pitch");
+    DRB_REQUIRE((reinterpret_cast<uintptr_t>(resid) & 15) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0,
+                "resid/gate not 16-byte aligned");
+  }
+  DRB_REQUIRE(cta_group >= 0 && cta_group <= 2, "cta_group must be 0, 1 or 2");
+  if (cta_group == 0) cta_group = (M > 128) ? 2 : 1;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, A, M, K, lda, kBlockM, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, kBlockN / cta_group, kBlockK);
+  if (rc) return rc;
+  GemmParams p{M, N, K, static_cast<__nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(resid), ldr,
+               static_cast<const __nv_bfloat16*>(gate)};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return cta_group == 1 ? dispatch_epi<1>(epilogue, ta, tb, p, s) : dispatch_epi<2>(epilogue, ta, tb, p, s);
+}

@@ -84,9 +84,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > DRB_WATCHDOG_NS) {
+#ifdef DRB_WATCHDOG_PRINTF
       printf("drb200 watchdog: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n",
              (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
+#endif
+      __trap();   // a protocol bug becomes a launch failure instead of a hung GPU
     }
   }
 }

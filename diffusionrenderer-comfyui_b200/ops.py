@@ -1,0 +1,159 @@
+"""Tensor-level wrappers over the C ABI: they validate device/dtype/contiguity, pull raw pointers and the current CUDA
+stream out of torch, and call libdrb200.so.  PyTorch is used for memory and streams only — no math happens here."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=BF16) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rows2d(t: torch.Tensor, name: str) -> int:
+    """row pitch (elements) of a 2-D tensor whose last dim is contiguous"""
+    if t.ndim != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name} must be 2-D with a contiguous last dimension")
+    return t.stride(0)
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_STORE,
+         resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, cta_group: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T).  `a`, `w`, `out`, `resid` may be row-strided views."""
+    _req(a, "a"), _req(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"shape mismatch: a {tuple(a.shape)} vs w {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=BF16)
+    _req(out, "out")
+    if tuple(out.shape) != (M, N):
+        raise ValueError("out has the wrong shape")
+    ldr = 0
+    if resid is not None:
+        _req(resid, "resid"), _req(gate, "gate")
+        ldr = _rows2d(resid, "resid")
+    _lib.call("drb_gemm_bf16", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), out.data_ptr(),
+              _rows2d(out, "out"), M, N, K, epilogue, _ptr(resid), ldr, _ptr(gate), cta_group, _stream())
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [Sq, H*128], k/v [Skv, H*128] (row-strided views of one qkv buffer are fine, same pitch) -> o [Sq, H*128]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, n)
+    ld = _rows2d(q, "q")
+    if _rows2d(k, "k") != ld or _rows2d(v, "v") != ld:
+        raise ValueError("q, k, v must share one row pitch")
+    if out is None:
+        out = torch.empty((q.shape[0], num_heads * 128), device=q.device, dtype=BF16)
+    _req(out, "out")
+    _lib.call("drb_attention_bf16", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), _rows2d(out, "out"),
+              q.shape[0], k.shape[0], num_heads, _stream())
+    return out
+
+
+def adaln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   add_gate: Optional[torch.Tensor] = None, add_vec: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x"), _req(shift, "shift"), _req(scale, "scale")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("drb_adaln_modulate", x.data_ptr(), out.data_ptr(), shift.data_ptr(), scale.data_ptr(), _ptr(add_gate),
+              _ptr(add_vec), rows, D, _stream())
+    return out
+
+
+def qk_norm_rope(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor,
+                 num_heads: int) -> torch.Tensor:
+    _req(qkv, "qkv"), _req(wq, "wq"), _req(wk, "wk"), _req(cos_tab, "cos_tab"), _req(sin_tab, "sin_tab")
+    _lib.call("drb_qk_norm_rope", qkv.data_ptr(), _rows2d(qkv, "qkv"), wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(),
+              sin_tab.data_ptr(), qkv.shape[0], num_heads, _stream())
+    return qkv
+
+
+def gemv(w: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None,
+         act: int = 0) -> torch.Tensor:
+    _req(w, "w"), _req(x, "x")
+    N, K = w.shape
+    if out is None:
+        out = torch.empty((N,), device=w.device, dtype=BF16)
+    _lib.call("drb_gemv_bf16", w.data_ptr(), _rows2d(w, "w"), x.data_ptr(), out.data_ptr(), _ptr(add), N, K, act, _stream())
+    return out
+
+
+def gemv_batched(w: torch.Tensor, x: torch.Tensor, out: torch.Tensor, add: Optional[torch.Tensor] = None, act: int = 0,
+                 n: Optional[int] = None) -> torch.Tensor:
+    """w [B,N,K] contiguous; x [K] (shared) or [B,K]; out [B,N]; add [N] (shared), [B,N] or None."""
+    _req(w, "w"), _req(x, "x"), _req(out, "out")
+    B, N, K = w.shape
+    n = N if n is None else n
+    x_bs = 0 if x.ndim == 1 else x.stride(0)
+    add_bs = 0 if (add is None or add.ndim == 1) else add.stride(0)
+    _lib.call("drb_gemv_bf16_batched", w.data_ptr(), w.stride(1), w.stride(0), x.data_ptr(), x_bs, out.data_ptr(),
+              out.stride(0), _ptr(add), add_bs, B, n, K, act, _stream())
+    return out
+
+
+def sigma_embedding(sigma: torch.Tensor, w_aff: torch.Tensor, e_out: torch.Tensor, emb_out: torch.Tensor) -> None:
+    _req(sigma, "sigma", torch.float32), _req(w_aff, "w_aff")
+    _lib.call("drb_sigma_embedding", sigma.data_ptr(), w_aff.data_ptr(), e_out.data_ptr(), emb_out.data_ptr(),
+              w_aff.numel(), _stream())
+
+
+def scale_patchify(x_t: torch.Tensor, sigma: torch.Tensor, tokens: torch.Tensor) -> None:
+    """x_t [C,T,H,W] bf16 contiguous -> tokens[:, 0:4C] (c_in-scaled)."""
+    _req(x_t, "x_t"), _req(sigma, "sigma", torch.float32), _req(tokens, "tokens")
+    C, T, H, W = x_t.shape
+    _lib.call("drb_scale_patchify", x_t.data_ptr(), sigma.data_ptr(), tokens.data_ptr(), _rows2d(tokens, "tokens"), C, T, H,
+              W, _stream())
+
+
+def patchify_condition(src: Optional[torch.Tensor], tokens: torch.Tensor, c0: int, T: int, H: int, W: int,
+                       ones_channel: int = -1, zero_from: Optional[int] = None) -> None:
+    _req(tokens, "tokens")
+    C = 0
+    if src is not None:
+        _req(src, "src")
+        C = src.shape[0]
+    ld = _rows2d(tokens, "tokens")
+    _lib.call("drb_patchify_condition", _ptr(src), tokens.data_ptr(), ld, c0, C, T, H, W, ones_channel,
+              ld if zero_from is None else zero_from, _stream())
+
+
+def unpatchify_euler(y_cond: torch.Tensor, y_uncond: Optional[torch.Tensor], guidance: float, sigma: torch.Tensor,
+                     sigma_next: torch.Tensor, x_t: torch.Tensor, x_next: torch.Tensor,
+                     f_out: Optional[torch.Tensor] = None) -> None:
+    _req(y_cond, "y_cond"), _req(x_t, "x_t"), _req(x_next, "x_next")
+    C, T, H, W = x_t.shape
+    _lib.call("drb_unpatchify_euler", y_cond.data_ptr(), _ptr(y_uncond), _rows2d(y_cond, "y_cond"), float(guidance),
+              sigma.data_ptr(), sigma_next.data_ptr(), x_t.data_ptr(), x_next.data_ptr(), _ptr(f_out), C, T, H, W, _stream())
+
+
+def postprocess_u8(video: torch.Tensor, normalize_normal: bool = False) -> torch.Tensor:
+    """video [3,T,H,W] bf16 -> uint8 [T,H,W,3]"""
+    _req(video, "video")
+    _, T, H, W = video.shape
+    out = torch.empty((T, H, W, 3), device=video.device, dtype=torch.uint8)
+    _lib.call("drb_postprocess_u8", video.data_ptr(), out.data_ptr(), T, H, W, int(bool(normalize_normal)), _stream())
+    return out
