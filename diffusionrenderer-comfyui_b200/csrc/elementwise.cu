@@ -269,7 +269,7 @@ unpatchify_euler_kernel(const __nv_bfloat16* __restrict__ yc, const __nv_bfloat1
                         __nv_bfloat16* __restrict__ F_out, int C, int T, int H, int W) {
   const int Hp = H >> 1, Wp = W >> 1;
   const int64_t total = static_cast<int64_t>(C) * T * Hp * Wp;
-  const float sg = *sigma, sn = *sigma_next;
+  const float sg = sigma ? *sigma : 1.0f, sn = sigma_next ? *sigma_next : 0.0f;
   const float sd = 0.5f;
   const float c_skip = (sd * sd) / (sg * sg + sd * sd);
   const float c_out = (sg * sd) / sqrtf(sg * sg + sd * sd);
@@ -292,17 +292,19 @@ unpatchify_euler_kernel(const __nv_bfloat16* __restrict__ yc, const __nv_bfloat1
       }
       f[q] = fc;
     }
-    const uint32_t x0 = *reinterpret_cast<const uint32_t*>(x_t + pix);
-    const uint32_t x1 = *reinterpret_cast<const uint32_t*>(x_t + pix + W);
-    const float xv[4] = {bf16_lo(x0), bf16_hi(x0), bf16_lo(x1), bf16_hi(x1)};
-    float o[4];
+    if (x_t != nullptr) {
+      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(x_t + pix);
+      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(x_t + pix + W);
+      const float xv[4] = {bf16_lo(x0), bf16_hi(x0), bf16_lo(x1), bf16_hi(x1)};
+      float o[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float den = c_skip * xv[q] + c_out * f[q];
-      o[q] = xv[q] + (xv[q] - den) / sg * dt;
+      for (int q = 0; q < 4; ++q) {
+        const float den = c_skip * xv[q] + c_out * f[q];
+        o[q] = xv[q] + (xv[q] - den) / sg * dt;
+      }
+      *reinterpret_cast<uint32_t*>(x_next + pix) = pack_bf16x2(o[0], o[1]);
+      *reinterpret_cast<uint32_t*>(x_next + pix + W) = pack_bf16x2(o[2], o[3]);
     }
-    *reinterpret_cast<uint32_t*>(x_next + pix) = pack_bf16x2(o[0], o[1]);
-    *reinterpret_cast<uint32_t*>(x_next + pix + W) = pack_bf16x2(o[2], o[3]);
     if (F_out != nullptr) {
       *reinterpret_cast<uint32_t*>(F_out + pix) = pack_bf16x2(f[0], f[1]);
       *reinterpret_cast<uint32_t*>(F_out + pix + W) = pack_bf16x2(f[2], f[3]);
@@ -339,6 +341,32 @@ postprocess_kernel(const __nv_bfloat16* __restrict__ video, uint8_t* __restrict_
       u = bf16_round(u * 255.0f);
       out[i * 3 + c] = static_cast<uint8_t>(u);   // truncating cast, like Tensor.to(torch.uint8)
     }
+  }
+}
+
+// ===================================================================== stand-alone EDM scheduler ops (public scheduler API)
+// mode 0: out = bf16(x * 1/sqrt(sigma^2 + 0.25))                 (model_diffusion_renderer.py:30-44)
+// mode 1: out = bf16(x + (x - (c_skip x + c_out F)) / sigma * (sigma_next - sigma))   (:46-82)
+__global__ void __launch_bounds__(256)
+edm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ F, const float* __restrict__ sigma,
+           const float* __restrict__ sigma_next, __nv_bfloat16* __restrict__ out, int64_t n, int mode) {
+  const float sg = *sigma;
+  const float sd = 0.5f;
+  const float cin = 1.0f / sqrtf(sg * sg + sd * sd);
+  const float c_skip = (sd * sd) / (sg * sg + sd * sd);
+  const float c_out = (sg * sd) / sqrtf(sg * sg + sd * sd);
+  const float dt = mode == 1 ? *sigma_next - sg : 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float xv = __bfloat162float(x[i]);
+    float o;
+    if (mode == 0) {
+      o = xv * cin;
+    } else {
+      const float den = c_skip * xv + c_out * __bfloat162float(F[i]);
+      o = xv + (xv - den) / sg * dt;
+    }
+    out[i] = __float2bfloat16_rn(o);
   }
 }
 
@@ -448,7 +476,10 @@ extern "C" int drb_patchify_condition(const void* src, void* tokens, int64_t ld_
 extern "C" int drb_unpatchify_euler(const void* y_cond, const void* y_uncond, int64_t ld_y, float guidance,
                                     const float* sigma, const float* sigma_next, const void* x_t, void* x_next,
                                     void* F_out, int C, int T, int H, int W, void* stream) {
-  DRB_REQUIRE(y_cond && sigma && sigma_next && x_t && x_next, "null pointer");
+  DRB_REQUIRE(y_cond, "null pointer");
+  DRB_REQUIRE((x_t == nullptr) == (x_next == nullptr), "x_t and x_next go together");
+  DRB_REQUIRE(x_t != nullptr || F_out != nullptr, "nothing to write: pass x_t/x_next and/or F_out");
+  DRB_REQUIRE(x_t == nullptr || (sigma && sigma_next), "the Euler update needs sigma and sigma_next");
   DRB_REQUIRE(C > 0 && T > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad latent shape");
   DRB_REQUIRE(ld_y >= 4 * C, "y pitch too small");
   const int64_t total = static_cast<int64_t>(C) * T * (H / 2) * (W / 2);
@@ -466,6 +497,24 @@ extern "C" int drb_postprocess_u8(const void* video, void* out_u8, int T, int H,
   const int64_t n_pix = static_cast<int64_t>(T) * H * W;
   postprocess_kernel<<<grid_for(n_pix, 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(video), static_cast<uint8_t*>(out_u8), n_pix, normalize_normal);
+  DRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int drb_edm_scale_input(const void* x, const float* sigma, void* out, int64_t n, void* stream) {
+  DRB_REQUIRE(x && sigma && out && n > 0, "null pointer or empty tensor");
+  edm_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), nullptr, sigma, nullptr, static_cast<__nv_bfloat16*>(out), n, 0);
+  DRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int drb_edm_euler_step(const void* model_output, const void* x, const float* sigma, const float* sigma_next,
+                                  void* out, int64_t n, void* stream) {
+  DRB_REQUIRE(model_output && x && sigma && sigma_next && out && n > 0, "null pointer or empty tensor");
+  edm_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(model_output), sigma, sigma_next,
+      static_cast<__nv_bfloat16*>(out), n, 1);
   DRB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -141,13 +141,37 @@ def patchify_condition(src: Optional[torch.Tensor], tokens: torch.Tensor, c0: in
               ld if zero_from is None else zero_from, _stream())
 
 
-def unpatchify_euler(y_cond: torch.Tensor, y_uncond: Optional[torch.Tensor], guidance: float, sigma: torch.Tensor,
-                     sigma_next: torch.Tensor, x_t: torch.Tensor, x_next: torch.Tensor,
-                     f_out: Optional[torch.Tensor] = None) -> None:
-    _req(y_cond, "y_cond"), _req(x_t, "x_t"), _req(x_next, "x_next")
-    C, T, H, W = x_t.shape
+def unpatchify_euler(y_cond: torch.Tensor, y_uncond: Optional[torch.Tensor], guidance: float,
+                     sigma: Optional[torch.Tensor], sigma_next: Optional[torch.Tensor], x_t: Optional[torch.Tensor],
+                     x_next: Optional[torch.Tensor], f_out: Optional[torch.Tensor] = None) -> None:
+    """y [S, 4C] -> F [C,T,H,W] (+ CFG) and, when x_t/x_next are given, the EDM Euler update x_t -> x_next."""
+    _req(y_cond, "y_cond")
+    ref = x_t if x_t is not None else f_out
+    if ref is None:
+        raise ValueError("pass x_t/x_next and/or f_out")
+    _req(ref, "x_t/f_out")
+    if not ref.is_contiguous():
+        raise ValueError("latent tensors must be contiguous [C,T,H,W]")
+    C, T, H, W = ref.shape
     _lib.call("drb_unpatchify_euler", y_cond.data_ptr(), _ptr(y_uncond), _rows2d(y_cond, "y_cond"), float(guidance),
-              sigma.data_ptr(), sigma_next.data_ptr(), x_t.data_ptr(), x_next.data_ptr(), _ptr(f_out), C, T, H, W, _stream())
+              _ptr(sigma), _ptr(sigma_next), _ptr(x_t), _ptr(x_next), _ptr(f_out), C, T, H, W, _stream())
+
+
+def edm_scale_input(x: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    _req(x, "x"), _req(sigma, "sigma", torch.float32)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.call("drb_edm_scale_input", x.data_ptr(), sigma.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def edm_euler_step(model_output: torch.Tensor, x: torch.Tensor, sigma: torch.Tensor, sigma_next: torch.Tensor) -> torch.Tensor:
+    _req(model_output, "model_output"), _req(x, "x"), _req(sigma, "sigma", torch.float32), _req(sigma_next, "sigma_next", torch.float32)
+    x, model_output = x.contiguous(), model_output.contiguous()
+    out = torch.empty_like(x)
+    _lib.call("drb_edm_euler_step", model_output.data_ptr(), x.data_ptr(), sigma.data_ptr(), sigma_next.data_ptr(),
+              out.data_ptr(), x.numel(), _stream())
+    return out
 
 
 def postprocess_u8(video: torch.Tensor, normalize_normal: bool = False) -> torch.Tensor:

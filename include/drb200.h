@@ -102,10 +102,19 @@ int drb_patchify_condition(const void* src, void* tokens, int64_t ld_tok, int c0
 /* Final unpatchify + Euler update (CleanGeneralDIT.py:709-716; model_diffusion_renderer.py:46-82, :232):
  * F[c,t,2h+ph,2w+pw] = y[s, (ph*2+pw)*C + c];  optional CFG  F = bf16(Fc + bf16(g * bf16(Fc - Fu)));
  * den = c_skip x + c_out F;  x_next = bf16(x + (x - den)/sigma * (sigma_next - sigma)), all fp32 inside.
- * y_cond / y_uncond: bf16 [S, ld_y]; x_t in / x_next out: bf16 [C,T,H,W] (may alias); F_out (nullable): bf16 [C,T,H,W]. */
+ * y_cond / y_uncond: bf16 [S, ld_y]; x_t in / x_next out: bf16 [C,T,H,W] (may alias); F_out (nullable): bf16 [C,T,H,W].
+ * x_t == x_next == NULL skips the Euler update (plain unpatchify into F_out; sigma pointers may then be NULL). */
 int drb_unpatchify_euler(const void* y_cond, const void* y_uncond, int64_t ld_y, float guidance, const float* sigma,
                          const float* sigma_next, const void* x_t, void* x_next, void* F_out, int C, int T, int H,
                          int W, void* stream);
+
+/* Stand-alone EDM scheduler ops on a flat bf16 tensor of n elements (the public CleanEDMEulerScheduler methods;
+ * the sampler loop itself uses the fused drb_scale_patchify / drb_unpatchify_euler):
+ *   scale_model_input: out = bf16(fp32(x) * 1/sqrt(sigma^2 + 0.25))                    model_diffusion_renderer.py:30-44
+ *   step:              out = bf16(x + (x - (c_skip x + c_out F)) / sigma * (sigma_next - sigma))         :46-82 */
+int drb_edm_scale_input(const void* x, const float* sigma, void* out, int64_t n, void* stream);
+int drb_edm_euler_step(const void* model_output, const void* x, const float* sigma, const float* sigma_next, void* out,
+                       int64_t n, void* stream);
 
 /* Decode post-process (diffusion_renderer_pipeline.py:300-318): optional normal re-normalisation blend, then
  * (1+v).clamp(0,2)/2*255 -> uint8 (truncating), BCTHW -> BTHWC.  video: bf16 [3,T,H,W]; out: uint8 [T,H,W,3]. */

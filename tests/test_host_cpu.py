@@ -1,0 +1,91 @@
+"""CPU tier: host logic of the product package and the C-ABI surface (no kernel is launched here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle.weights import FULL_FORWARD, FULL_INVERSE, MICRO_FORWARD, MICRO_INVERSE, TINY_INVERSE, net_param_shapes
+from tests.util import model_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from drb200 import _lib
+    header = open(os.path.join(ROOT, "include", "drb200.h")).read()
+    declared = set(re.findall(r"\b(drb_[a-z0-9_]+)\s*\(", header))
+    assert {"drb_gemm_bf16", "drb_attention_bf16", "drb_adaln_modulate", "drb_unpatchify_euler"} <= declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/drb200.h but not exported"
+    bound = set(_lib.PROTOTYPES) | {"drb_last_error", "drb_version", "drb_device_supported"}
+    assert declared == bound, f"ctypes binding out of sync with the header: {declared ^ bound}"
+    assert _lib.load().drb_version() >= 100
+
+
+def test_invalid_arguments_raise_valueerror_without_a_gpu():
+    from drb200 import _lib
+    with pytest.raises(ValueError):
+        _lib.call("drb_gemm_bf16", None, 8, None, 8, None, 8, 1, 8, 8, 0, None, 0, None, 0, None)
+    with pytest.raises(ValueError):
+        _lib.call("drb_adaln_modulate", 16, 16, 16, 16, None, None, 4, 100, None)   # D not a multiple of 256
+
+
+@pytest.mark.parametrize("dims,mt", [(MICRO_INVERSE, "inverse"), (MICRO_FORWARD, "forward"), (TINY_INVERSE, "inverse")])
+def test_state_dict_keys_and_shapes_match_reference_layout(dims, mt):
+    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
+    model = CleanDiffusionRendererModel(model_config(dims, mt))
+    sd = model.state_dict()
+    want = {k: tuple(s) for k, s, _ in net_param_shapes(dims)}
+    assert set(sd) == set(want)
+    for k, s in want.items():
+        assert tuple(sd[k].shape) == s, k
+
+
+@pytest.mark.parametrize("dims,mt,n", [(FULL_INVERSE, "inverse", 572), (FULL_FORWARD, "forward", 571)])
+def test_full_size_key_count_on_meta_device(dims, mt, n):
+    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
+    with torch.device("meta"):
+        model = CleanDiffusionRendererModel(model_config(dims, mt, 704, 1280, 57))
+    sd = model.state_dict()
+    assert len(sd) == n                                    # SURVEY.md §8b [PROBED: 572 / 571 entries]
+    net_params = sum(v.numel() for k, v in sd.items() if k.startswith("net.") and k != "net.pos_embedder.seq")
+    assert net_params == (7_234_963_456 if mt == "inverse" else 7_236_913_152)
+
+
+def test_cpu_forward_fails_loudly():
+    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
+    model = CleanDiffusionRendererModel(model_config(MICRO_INVERSE, "inverse"))
+    x = torch.zeros(1, 16, 2, 8, 12)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.net(x, torch.tensor(1.0), x, torch.zeros(1, 1, dtype=torch.long))
+
+
+def test_config_matches_reference_values():
+    from drb200 import diffusion_renderer_config as cfg
+    inv = cfg.get_inverse_renderer_config()
+    fwd = cfg.get_forward_renderer_config()
+    assert inv["condition_keys"] == ["rgb"] and inv["append_condition_mask"] is False
+    assert inv["net"]["additional_concat_ch"] == 16 and inv["net"]["use_context_embedding"] is True
+    assert fwd["net"]["additional_concat_ch"] == 136 and fwd["net"]["use_context_embedding"] is False
+    assert len(fwd["condition_keys"]) == 8 and fwd["append_condition_mask"] is True
+    assert inv["latent_shape"] == [16, 8, 88, 160]
+    assert inv["scheduler"]["sigma_max"] == 80.0 and inv["scheduler"]["sigma_min"] == 0.02
+    cfg.validate_config(inv)
+    with pytest.raises(ValueError):
+        cfg.get_config_from_tensor_shape("inverse", (1, 3, 704, 1280))
+    with pytest.raises(ValueError):
+        cfg.validate_config({k: v for k, v in inv.items() if k != "net"})
+
+
+def test_scheduler_sigmas_match_oracle():
+    from drb200.model_diffusion_renderer import CleanEDMEulerScheduler
+    from oracle.sampler_oracle import sigma_schedule
+    s = CleanEDMEulerScheduler()
+    s.set_timesteps(15)
+    assert torch.equal(s.sigmas, sigma_schedule(15))
+    assert s.timesteps.numel() == 15 and s.sigmas[-1] == 0
+    with pytest.raises(RuntimeError):
+        CleanEDMEulerScheduler().step(torch.zeros(1), torch.tensor(1.0), torch.zeros(1))

@@ -1,0 +1,228 @@
+"""GPU unit parity of every sm_100a kernel behind the C ABI against the oracle's op-level functions (torch, same GPU).
+
+bf16 GEMM / attention: relative L2 vs an fp32 reference <= 3e-3 (GEMM, bf16 output rounding ~2e-3 worst case) and
+<= 5e-3 (attention; P is rounded to bf16 before P.V as in every flash kernel).  Elementwise kernels round where the
+reference's chain of bf16 tensor ops rounds, so they are compared for (near) bit-equality: at most 1 bf16 ulp on a
+small fraction of elements (transcendental / reduction-order differences), stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dit_oracle as do
+from oracle import sampler_oracle as so
+from oracle.weights import DitDims
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def gen(seed=0):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def assert_close_bf16(got, ref, max_ulp=1, min_exact=0.98):
+    """|got - ref| <= max_ulp bf16 ulps of max(|ref|, max|ref| / 64): elements that are small through cancellation
+    carry the absolute fp32 accumulation-order noise of the large terms they were summed from."""
+    got, ref = got.float(), ref.float()
+    tol = ref.abs().clamp_min(ref.abs().max() / 64) * (2.0 ** -7) * max_ulp     # 1 bf16 ulp <= 2^-7 |x|
+    bad = (got - ref).abs() > tol
+    assert not bad.any(), f"{int(bad.sum())} elements differ by more than {max_ulp} bf16 ulp"
+    exact = (got == ref).float().mean().item()
+    assert exact >= min_exact, f"only {exact:.4f} of the elements are bit-equal"
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 520, 136), (48, 64, 256), (1000, 768, 616), (2048, 512, 2048)])
+def test_gemm_store(cg, M, N, K):
+    from drb200 import ops
+    g = gen(1)
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    out = ops.gemm(a, w, cta_group=cg)
+    ref = a.float() @ w.float().t()
+    assert rel_l2(out, ref) <= 3e-3
+    assert_close_bf16(out, ref.bfloat16(), max_ulp=1, min_exact=0.97)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_strided_views_and_epilogues(cg):
+    from drb200 import ops
+    g = gen(2)
+    M, N, K = 640, 512, 384
+    big = (torch.randn(M, 3 * K, device=DEV, generator=g) * 0.5).bfloat16()
+    a = big[:, K:2 * K]                                               # row-strided view (like q/k/v of one buffer)
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    acc = (a.float() @ w.float().t()).bfloat16()
+    # acc itself may differ by 1 bf16 ulp (fp32 accumulation order), which the epilogue math can amplify slightly
+    assert_close_bf16(ops.gemm(a, w, epilogue=1, cta_group=cg), F.gelu(acc), max_ulp=2, min_exact=0.95)
+    resid = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    gate = torch.randn(N, device=DEV, generator=g).bfloat16()
+    ref = resid + gate[None, :] * acc
+    x = resid.clone()
+    ops.gemm(a, w, out=x, epilogue=2, resid=x, gate=gate, cta_group=cg)   # in place, as the DiT uses it
+    assert_close_bf16(x, ref, max_ulp=4, min_exact=0.95)
+
+
+def test_gemm_rejects_bad_arguments():
+    from drb200 import ops
+    a = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.gemm(a, w)                                                # K not a multiple of 8
+    with pytest.raises(ValueError):
+        ops.gemm(a.float(), w)
+    with pytest.raises(ValueError):
+        ops.gemm(a.cpu(), w.cpu())
+
+
+@pytest.mark.parametrize("S,Skv,H", [(128, 128, 1), (512, 512, 4), (48, 48, 2), (1000, 1000, 2), (300, 700, 3), (4096, 4096, 2)])
+def test_attention(S, Skv, H):
+    from drb200 import ops
+    g = gen(3)
+    qkv = torch.randn(max(S, Skv), 3 * H * 128, device=DEV, generator=g).bfloat16()
+    q, k, v = qkv[:S, :H * 128], qkv[:Skv, H * 128:2 * H * 128], qkv[:Skv, 2 * H * 128:]
+    out = ops.attention(q, k, v, H)
+    q4 = q.float().reshape(S, H, 128).permute(1, 0, 2)[None]
+    k4 = k.float().reshape(Skv, H, 128).permute(1, 0, 2)[None]
+    v4 = v.float().reshape(Skv, H, 128).permute(1, 0, 2)[None]
+    ref = F.scaled_dot_product_attention(q4, k4, v4)[0].permute(1, 0, 2).reshape(S, H * 128)
+    assert rel_l2(out, ref) <= 5e-3
+    # against the reference's own bf16 SDPA call (CleanGeneralDIT.py:192-197)
+    ref16 = F.scaled_dot_product_attention(q4.bfloat16(), k4.bfloat16(), v4.bfloat16())[0].permute(1, 0, 2).reshape(S, H * 128)
+    assert rel_l2(out, ref16) <= 8e-3
+
+
+def test_attention_large_logits_rescale_path():
+    """row maxima that keep growing along kv force the lazy O-rescale branch"""
+    from drb200 import ops
+    g = gen(4)
+    S, H = 1024, 1
+    q = torch.randn(S, 128, device=DEV, generator=g).bfloat16() * 4
+    k = torch.randn(S, 128, device=DEV, generator=g).bfloat16()
+    k = (k * torch.linspace(0.2, 6.0, S, device=DEV)[:, None]).bfloat16()      # later keys -> larger |logits|
+    v = torch.randn(S, 128, device=DEV, generator=g).bfloat16()
+    out = ops.attention(q, k, v, H)
+    ref = F.scaled_dot_product_attention(q.float()[None, None], k.float()[None, None], v.float()[None, None])[0, 0]
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) <= 8e-3
+
+
+@pytest.mark.parametrize("D", [256, 512, 4096])
+@pytest.mark.parametrize("with_add", [False, True])
+def test_adaln_modulate(D, with_add):
+    from drb200 import ops
+    g = gen(5)
+    rows = 77
+    x = (torch.randn(rows, D, device=DEV, generator=g) * 3 + 0.5).bfloat16()
+    shift = torch.randn(D, device=DEV, generator=g).bfloat16()
+    scale = torch.randn(D, device=DEV, generator=g).bfloat16()
+    gate = torch.randn(D, device=DEV, generator=g).bfloat16()
+    vec = torch.randn(D, device=DEV, generator=g).bfloat16()
+    xin = x.clone()
+    if with_add:
+        out = ops.adaln_modulate(xin, shift, scale, add_gate=gate, add_vec=vec)
+        x_ref = x + gate[None] * vec[None]
+        assert torch.equal(xin, x_ref)                                # residual stream updated in place, bit-exact
+    else:
+        out = ops.adaln_modulate(xin, shift, scale)
+        x_ref = x
+    ref = F.layer_norm(x_ref, (D,), eps=1e-6) * (1 + scale[None]) + shift[None]
+    assert_close_bf16(out, ref, max_ulp=2, min_exact=0.97)
+
+
+@pytest.mark.parametrize("H", [2, 32])
+def test_qk_norm_rope(H):
+    from drb200 import ops
+    from drb200.CleanGeneralDIT import _RoPE3D
+    g = gen(6)
+    T, Hp, Wp = 2, 5, 7
+    S, D = T * Hp * Wp, H * 128
+    qkv = torch.randn(S, 3 * D, device=DEV, generator=g).bfloat16()
+    wq = (1 + 0.1 * torch.randn(128, device=DEV, generator=g)).bfloat16()
+    wk = (1 + 0.1 * torch.randn(128, device=DEV, generator=g)).bfloat16()
+    dims = DitDims(model_channels=D, num_heads=H)
+    ang = do.rope_angles(dims, T, Hp, Wp, torch.bfloat16, DEV)
+    cos, sin = _RoPE3D(128).to(DEV).to(torch.bfloat16).tables(T, Hp, Wp, torch.bfloat16)
+    assert torch.equal(cos, ang.cos()) and torch.equal(sin, ang.sin())   # host table == reference's bf16-angle quirk
+    ref_q = do.apply_rope(do.rms_norm(qkv[:, :D].reshape(S, 1, H, 128), wq), ang).reshape(S, D)
+    ref_k = do.apply_rope(do.rms_norm(qkv[:, D:2 * D].reshape(S, 1, H, 128), wk), ang).reshape(S, D)
+    v_before = qkv[:, 2 * D:].clone()
+    ops.qk_norm_rope(qkv, wq, wk, cos, sin, H)
+    assert torch.equal(qkv[:, 2 * D:], v_before)
+    assert_close_bf16(qkv[:, :D], ref_q, max_ulp=2, min_exact=0.97)
+    assert_close_bf16(qkv[:, D:2 * D], ref_k, max_ulp=2, min_exact=0.97)
+
+
+def test_gemv_and_sigma_embedding():
+    from drb200 import ops
+    g = gen(7)
+    D = 512
+    w = (torch.randn(3 * D, D, device=DEV, generator=g) / math.sqrt(D)).bfloat16()
+    x = torch.randn(D, device=DEV, generator=g).bfloat16()
+    add = torch.randn(3 * D, device=DEV, generator=g).bfloat16()
+    assert_close_bf16(ops.gemv(w, x), F.linear(x[None], w)[0], max_ulp=1, min_exact=0.9)
+    assert_close_bf16(ops.gemv(w, x, add=add, act=1), F.linear(F.silu(x)[None], w)[0] + add, max_ulp=1, min_exact=0.9)
+    wb = (torch.randn(5, 3 * D, 256, device=DEV, generator=g) / 16).bfloat16()
+    xb = torch.randn(5, 256, device=DEV, generator=g).bfloat16()
+    out = torch.empty(5, 3 * D, device=DEV, dtype=torch.bfloat16)
+    ops.gemv_batched(wb, xb, out, add=add)
+    ref = torch.einsum("bnk,bk->bn", wb.float(), xb.float()).bfloat16() + add[None]
+    assert_close_bf16(out, ref, max_ulp=1, min_exact=0.9)
+    w_aff = (1 + 0.1 * torch.randn(D, device=DEV, generator=g)).bfloat16()
+    for s in (80.0, 3.17, 0.02):
+        sig = torch.tensor([s], device=DEV)
+        e, emb = torch.empty(D, device=DEV, dtype=torch.bfloat16), torch.empty(D, device=DEV, dtype=torch.bfloat16)
+        ops.sigma_embedding(sig, w_aff, e, emb)
+        ref_e = do.sigma_embedding(sig.bfloat16(), D)[0]
+        assert_close_bf16(e, ref_e, max_ulp=1, min_exact=0.9)
+        assert_close_bf16(emb, do.rms_norm(ref_e[None], w_aff)[0], max_ulp=1, min_exact=0.9)
+
+
+def test_patchify_unpatchify_euler():
+    from drb200 import ops
+    g = gen(8)
+    C, T, H, W, Cc = 16, 2, 8, 12, 16
+    S = T * (H // 2) * (W // 2)
+    x = (torch.randn(C, T, H, W, device=DEV, generator=g) * 20).bfloat16()
+    cond = torch.randn(Cc, T, H, W, device=DEV, generator=g).bfloat16()
+    sig, nxt = torch.tensor([7.3], device=DEV), torch.tensor([2.9], device=DEV)
+    kdim = (C + Cc + 1) * 4
+    tok = torch.full((S, kdim + 4), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.patchify_condition(cond, tok, C, T, H, W, ones_channel=C + Cc, zero_from=kdim)
+    ops.scale_patchify(x, sig, tok)
+    xin = so.scale_model_input(x[None], sig[0])
+    full = torch.cat([xin, cond[None], torch.ones(1, 1, T, H, W, device=DEV, dtype=torch.bfloat16)], dim=1)
+    ref = do.patchify(full, 2).reshape(S, kdim)
+    assert torch.equal(tok[:, :kdim], ref) and (tok[:, kdim:] == 0).all()
+    y = torch.randn(S, 4 * C, device=DEV, generator=g).bfloat16()
+    yu = torch.randn(S, 4 * C, device=DEV, generator=g).bfloat16()
+    f_ref = do.unpatchify(y, 1, T, H // 2, W // 2, 2, C)
+    f_out = torch.empty(C, T, H, W, device=DEV, dtype=torch.bfloat16)
+    ops.unpatchify_euler(y, None, 0.0, None, None, None, None, f_out=f_out)
+    assert torch.equal(f_out[None], f_ref)
+    x_next = torch.empty_like(x)
+    ops.unpatchify_euler(y, None, 0.0, sig, nxt, x, x_next)
+    assert_close_bf16(x_next[None], so.euler_step(f_ref, sig[0], nxt[0], x[None]), max_ulp=1, min_exact=0.98)
+    fu = do.unpatchify(yu, 1, T, H // 2, W // 2, 2, C)
+    f_cfg = f_ref + 2.0 * (f_ref - fu)
+    ops.unpatchify_euler(y, yu, 2.0, sig, nxt, x, x_next, f_out=f_out)
+    assert torch.equal(f_out[None], f_cfg)
+    assert_close_bf16(x_next[None], so.euler_step(f_cfg, sig[0], nxt[0], x[None]), max_ulp=1, min_exact=0.98)
+    last = torch.zeros(1, device=DEV)
+    ops.unpatchify_euler(y, None, 0.0, sig, last, x, x_next)          # sigma_next = 0: x_next = denoised
+    assert_close_bf16(x_next[None], so.euler_step(f_ref, sig[0], last[0], x[None]), max_ulp=1, min_exact=0.98)
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_postprocess_u8(normalize):
+    from drb200 import ops
+    g = gen(9)
+    v = (torch.randn(1, 3, 3, 16, 24, device=DEV, generator=g) * 0.8).bfloat16()
+    got = ops.postprocess_u8(v[0], normalize).cpu().numpy()
+    ref = so.postprocess(v, normalize)[0]
+    diff = abs(got.astype(int) - ref.astype(int))
+    assert diff.max() <= (2 if normalize else 0)      # plain path is bit-exact; the normal blend may move 1 bf16 ulp
+    assert (diff == 0).mean() >= 0.97
