@@ -7,7 +7,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdrb200.so")
+LIB_PATH = os.environ.get("DRB200_LIB", os.path.join(HERE, "libdrb200.so"))   # override: tuning builds only
 
 DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_UNSUPPORTED = 0, -1, -2, -3
 EPI_STORE, EPI_GELU, EPI_GATED_RESIDUAL = 0, 1, 2

@@ -14,6 +14,8 @@
 // does itself between s_full and p_full, when O_t is quiescent.
 //
 // Roofline: tensor pipe, 4*q_len*kv_len*128 flop per head.
+#include <stdlib.h>
+
 #include "../../include/drb200.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -41,8 +43,69 @@ struct AttnParams {
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // not volatile: ptxas may batch the MUFUs
   return y;
+}
+
+// ---- packed fp32x2 arithmetic (one issue slot for two lanes of work on sm_100) and the FMA-pipe exp2
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for two values on the FMA pipe (the MUFU unit is the co-bottleneck of the softmax):
+// n = round(x) by the 1.5*2^23 trick, f = x - n in [-0.5, 0.5], degree-3 polynomial (max rel. error 2.4e-4, an order
+// of magnitude below the bf16 rounding P receives), exponent patched in with one integer shift-add.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& r0, float& r1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f), neg_magic = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t xr = add2(x2, magic);
+  const uint64_t nf = add2(xr, neg_magic);
+  const uint64_t f = fma2(nf, pack2(-1.0f, -1.0f), x2);
+  uint64_t p = fma2(pack2(0.05273903161287308f, 0.05273903161287308f), f, pack2(0.24209719896316528f, 0.24209719896316528f));
+  p = fma2(p, f, pack2(0.6935965418815613f, 0.6935965418815613f));
+  p = fma2(p, f, pack2(0.9999658465385437f, 0.9999658465385437f));
+  float p0, p1, n0, n1;
+  unpack2(p, p0, p1);
+  unpack2(xr, n0, n1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(n0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(n1) << 23));
+}
+// kPolyMask: which key pairs (index i within a 32-column chunk, 16 pairs) take the polynomial instead of MUFU.EX2
+// P for one 32-column chunk of S: 16 packed bf16x2 words into pk[], partial row sums into sum2
+template <uint32_t kPolyMask>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], uint64_t scale2, uint64_t negm2, uint32_t* pk,
+                                              uint64_t& sum2) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint64_t x2 = fma2(pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), scale2, negm2);
+    float a, b;
+    if ((kPolyMask >> i) & 1u) {
+      exp2_poly2(x2, a, b);
+    } else {
+      float x0, x1;
+      unpack2(x2, x0, x1);
+      a = ex2(x0);
+      b = ex2(x1);
+    }
+    sum2 = add2(sum2, pack2(a, b));
+    pk[i] = pack_bf16x2(a, b);
+  }
 }
 
 template <int kRegs>
@@ -59,6 +122,19 @@ constexpr uint32_t kLoMnMajor = (kBoxBytes >> 4) << 16;                // LBO = 
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; }
 __device__ __forceinline__ constexpr uint32_t kstep_off(int k) { return ((k >> 2) * kBoxBytes + (k & 3) * 32) >> 4; }
 
+#ifdef DRB_ATTN_PROFILE
+// phase cycle counters of CTA (0,0): [0..7] softmax warp 4, [8..15] MMA thread (tuning builds only)
+__device__ unsigned long long g_attn_prof[16];
+#define PROF_DECL unsigned long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF(i) do { unsigned long long _n = clock64(); prof_acc[i] += _n - prof_t; prof_t = _n; } while (0)
+#define PROF_DUMP(base) do { if (blockIdx.x == 0 && blockIdx.y == 0) for (int _i = 0; _i < 8; ++_i) g_attn_prof[(base) + _i] = prof_acc[_i]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_DUMP(base)
+#endif
+
+template <uint32_t kPolyMask>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -71,8 +147,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + kKvSlots;
   uint64_t* s_full = kv_empty + kKvSlots;   // [2]
-  uint64_t* p_full = s_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 2);
+  uint64_t* p_full = s_full + 2;            // [2 tiles][2 halves of the key range]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 4);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,7 +169,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);   // one arrival per softmax warp
+      mbar_init(&p_full[2 * t], 4);   // one arrival per softmax warp
+      mbar_init(&p_full[2 * t + 1], 4);
     }
     fence_barrier_init();
   }
@@ -127,11 +204,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tma_load_2d(dst + kBoxBytes, tm, &kv_full[slot], col + 64, row);
         if (++slot == kKvSlots) { slot = 0; phase ^= 1; }
       }
-    } else if (warp_idx == 1 && lane == 0) {
+    } else if (warp_idx == 1) {
       // ---------------------------------------------------------------- MMA issuer
+      // The WHOLE warp runs this loop in uniform control flow and one elected lane issues: the descriptors then live
+      // in uniform registers, which is what UTCHMMA reads (a lane-divergent loop costs an R2UR round trip per operand
+      // and made the issue thread, not the tensor pipe, the bottleneck: 80 cycles per MMA measured).
       constexpr uint32_t idesc_qk = make_idesc_bf16(kTileQ, kTileKV, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kTileQ, kHeadDim, false, true);   // B = V is MN-major
-      uint32_t q_lo = ((smem_u32(smem_q) & 0x3FFFF) >> 4) | kLoKMajor;
+      const bool leader = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t q_lo = ((smem_u32(smem_q) & 0x3FFFF) >> 4) | kLoKMajor;
       const uint32_t kv_lo = ((smem_u32(smem_kv) & 0x3FFFF) >> 4) | kLoKMajor;
       const uint32_t v_lo = ((smem_u32(smem_kv) & 0x3FFFF) >> 4) | kLoMnMajor;
       int slot = 0;
@@ -139,21 +221,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[slot], phase);
       tc_fence_after();
-      for (int t = 0; t < 2; ++t) {
 #pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_ss<1>(tmem_base + t * 128, desc64(q_lo + t * (kTileBytes >> 4) + kstep_off(k)),
-                     desc64(kv_lo + slot * (kTileBytes >> 4) + kstep_off(k)), idesc_qk, k != 0);
-        umma_commit(&s_full[t]);
+      for (int t = 0; t < 2; ++t) {
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_ss<1>(tm + t * 128, desc64(q_lo + t * (kTileBytes >> 4) + kstep_off(k)),
+                       desc64(kv_lo + slot * (kTileBytes >> 4) + kstep_off(k)), idesc_qk, k != 0);
+          umma_commit(&s_full[t]);
+        }
       }
-      umma_commit(&kv_empty[slot]);
+      if (leader) umma_commit(&kv_empty[slot]);
+      __syncwarp();
       if (++slot == kKvSlots) { slot = 0; phase ^= 1; }
+      PROF_DECL;
       for (int j = 0; j < n_kv; ++j) {
         const int v_slot = slot;
+        PROF(0);
         mbar_wait(&kv_full[v_slot], phase);
         if (++slot == kKvSlots) { slot = 0; phase ^= 1; }
         const bool more = j + 1 < n_kv;
-        asm volatile("" : "+r"(q_lo));   // keep the 16 Q descriptors out of (spilled) loop-invariant registers
         int k_slot = 0;
         if (more) {
           k_slot = slot;
@@ -161,26 +248,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (++slot == kKvSlots) { slot = 0; phase ^= 1; }
         }
         tc_fence_after();
+        PROF(1);
+        const uint32_t v_desc = v_lo + v_slot * (kTileBytes >> 4);
+        const uint32_t k_desc = kv_lo + k_slot * (kTileBytes >> 4);
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          tc_fence_after();
           // O_t (+)= P_t V_j : A = P_t (bf16 pairs packed in TMEM columns, 8 columns per k-step of 16),
-          //                    B = 16 rows of V (2048 B) x 128 columns (two 64-wide chunks 16 KB apart)
+          //                    B = 16 rows of V (2048 B) x 128 columns (two 64-wide chunks 16 KB apart).
+          // P arrives in two halves (keys 0..63, 64..127) so the first four k-steps overlap the rest of the softmax.
 #pragma unroll
-          for (int k = 0; k < kTileKV / 16; ++k)
-            umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
-                    desc64(v_lo + v_slot * (kTileBytes >> 4) + k * (2048 >> 4)), idesc_pv, (j | k) != 0);
-          if (t == 1) umma_commit(&kv_empty[v_slot]);
-          if (more) {
+          for (int half = 0; half < 2; ++half) {
+            PROF(2);
+            mbar_wait(&p_full[2 * t + half], j & 1);
+            tc_fence_after();
+            PROF(3 + half);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < kHeadDim / 16; ++k)
-              umma_ss<1>(tmem_base + t * 128, desc64(q_lo + t * (kTileBytes >> 4) + kstep_off(k)),
-                         desc64(kv_lo + k_slot * (kTileBytes >> 4) + kstep_off(k)), idesc_qk, k != 0);
+              for (int k = half * 4; k < half * 4 + 4; ++k)
+                umma_ts(tm + 256 + t * 128, tm + t * 128 + k * 8, desc64(v_desc + k * (2048 >> 4)), idesc_pv, (j | k) != 0);
+            }
           }
-          umma_commit(&s_full[t]);   // S_t(j+1) ready (and P_t V_j done); after the last tile: O_t final
-          if (more && t == 1) umma_commit(&kv_empty[k_slot]);
+          if (leader) {
+            if (t == 1) umma_commit(&kv_empty[v_slot]);
+            if (more) {
+#pragma unroll
+              for (int k = 0; k < kHeadDim / 16; ++k)
+                umma_ss<1>(tm + t * 128, desc64(q_lo + t * (kTileBytes >> 4) + kstep_off(k)), desc64(k_desc + kstep_off(k)),
+                           idesc_qk, k != 0);
+            }
+            umma_commit(&s_full[t]);   // S_t(j+1) ready (and P_t V_j done); after the last tile: O_t final
+            if (more && t == 1) umma_commit(&kv_empty[k_slot]);
+          }
+          __syncwarp();
         }
       }
+      PROF(0);
+      PROF_DUMP(8);
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
@@ -190,88 +293,112 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_off + t * 128;
     const uint32_t o_tmem = tmem_base + lane_off + 256 + t * 128;
-    float m_ref = 0.f, l = 0.f;
+    float m_ref = -INFINITY, l = 0.f;
+    PROF_DECL;
     for (int j = 0; j < n_kv; ++j) {
+      PROF(0);
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      PROF(1);
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld32(s_tmem, s0);
       tmem_ld32(s_tmem + 32, s1);
-      tmem_ld32(s_tmem + 64, s2);
-      tmem_ld32(s_tmem + 96, s3);
       tmem_wait_ld();
+      tmem_ld32(s_tmem + 64, s2);       // in flight while the first half is exponentiated
+      tmem_ld32(s_tmem + 96, s3);
       const int valid = p.kv_len - j * kTileKV;    // >= 128 except on a ragged last tile
       if (valid < kTileKV) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= valid) s0[i] = 0xff800000u;
           if (32 + i >= valid) s1[i] = 0xff800000u;
+        }
+      }
+      // SPECULATIVE exponentials: P is computed against the running reference maximum m_ref of the previous tiles
+      // while this tile's row maximum is reduced alongside (independent instructions that fill the issue slots the
+      // MUFU-bound exponentials leave free).  Only if the maximum grew by more than 2^8 (rare after the first tiles;
+      // always on j == 0, where m_ref = -inf) is the work redone against the new reference, after rescaling O_t.
+      const uint64_t scale2 = pack2(kScaleLog2, kScaleLog2);
+      uint64_t negm2 = pack2(-m_ref * kScaleLog2, -m_ref * kScaleLog2);
+      uint64_t sum_a = pack2(0.f, 0.f), sum_b = pack2(0.f, 0.f);
+      uint32_t pk[32], pk2[32];
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
+      }
+      softmax_chunk<kPolyMask>(s0, scale2, negm2, pk, sum_a);
+      softmax_chunk<kPolyMask>(s1, scale2, negm2, pk + 16, sum_b);
+      tmem_st32(s_tmem, pk);        // P_t columns [0,32): keys 0..63
+      PROF(2);
+      tmem_wait_ld();
+      if (valid < kTileKV) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
           if (64 + i >= valid) s2[i] = 0xff800000u;
           if (96 + i >= valid) s3[i] = 0xff800000u;
         }
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
-        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      for (int i = 0; i < 32; i += 2) {
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s2[i + 1])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s3[i]), __uint_as_float(s3[i + 1])));
       }
-      const float m_cur = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if (j == 0) {
-        m_ref = m_cur;
-      } else {
-        const float m_new = fmaxf(m_ref, m_cur);
+      softmax_chunk<kPolyMask>(s2, scale2, negm2, pk2, sum_a);
+      PROF(3);
+      {
+        const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
         const bool grow = (m_new - m_ref) * kScaleLog2 > kRescaleThreshold;
         if (__any_sync(0xffffffffu, grow)) {
-          // rescale the running sum and this row of O_t (quiescent: P_t V_{j-1} completed before s_full fired)
+          // slow path: new reference; rescale the running sum and this row of O_t (quiescent: P_t V_{j-1} completed
+          // before s_full fired), then redo the three speculative chunks
           const float alpha = ex2((m_ref - m_new) * kScaleLog2);
           l *= alpha;
           m_ref = m_new;
+          if (j > 0) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld32(o_tmem + c * 32, o);
-            tmem_wait_ld();
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(o_tmem + c * 32, o);
+              tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(o_tmem + c * 32, o);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o_tmem + c * 32, o);
+            }
           }
+          negm2 = pack2(-m_ref * kScaleLog2, -m_ref * kScaleLog2);
+          sum_a = pack2(0.f, 0.f);
+          sum_b = pack2(0.f, 0.f);
+          softmax_chunk<kPolyMask>(s0, scale2, negm2, pk, sum_a);
+          softmax_chunk<kPolyMask>(s1, scale2, negm2, pk + 16, sum_b);
           tmem_wait_st();
+          tmem_st32(s_tmem, pk);
+          softmax_chunk<kPolyMask>(s2, scale2, negm2, pk2, sum_a);
         }
       }
-      const float neg_m = -m_ref * kScaleLog2;
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      uint32_t pk[32];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = ex2(fmaf(__uint_as_float(s0[2 * i]), kScaleLog2, neg_m));
-        const float b = ex2(fmaf(__uint_as_float(s0[2 * i + 1]), kScaleLog2, neg_m));
-        const float c = ex2(fmaf(__uint_as_float(s1[2 * i]), kScaleLog2, neg_m));
-        const float d = ex2(fmaf(__uint_as_float(s1[2 * i + 1]), kScaleLog2, neg_m));
-        sum0 += a; sum1 += b; sum2 += c; sum3 += d;
-        pk[i] = pack_bf16x2(a, b);
-        pk[16 + i] = pack_bf16x2(c, d);
+      PROF(4);
+      tmem_wait_st();               // first half landed while chunk 2 was computed: hand it to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[2 * t]);
+      PROF(5);
+      softmax_chunk<kPolyMask>(s3, scale2, negm2, pk2 + 16, sum_b);
+      tmem_st32(s_tmem + 32, pk2);  // P_t columns [32,64): keys 64..127
+      PROF(6);
+      {
+        float a0, a1, b0, b1;
+        unpack2(sum_a, a0, a1);
+        unpack2(sum_b, b0, b1);
+        l += (a0 + a1) + (b0 + b1);
       }
-      tmem_st32(s_tmem, pk);        // P_t columns [0,32): keys 0..63
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = ex2(fmaf(__uint_as_float(s2[2 * i]), kScaleLog2, neg_m));
-        const float b = ex2(fmaf(__uint_as_float(s2[2 * i + 1]), kScaleLog2, neg_m));
-        const float c = ex2(fmaf(__uint_as_float(s3[2 * i]), kScaleLog2, neg_m));
-        const float d = ex2(fmaf(__uint_as_float(s3[2 * i + 1]), kScaleLog2, neg_m));
-        sum0 += a; sum1 += b; sum2 += c; sum3 += d;
-        pk[i] = pack_bf16x2(a, b);
-        pk[16 + i] = pack_bf16x2(c, d);
-      }
-      tmem_st32(s_tmem + 32, pk);   // P_t columns [32,64): keys 64..127
-      l += (sum0 + sum1) + (sum2 + sum3);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(&p_full[2 * t + 1]);
+      PROF(7);
     }
+    if (warp_idx == 4 && lane == 0) PROF_DUMP(0);
     // ---- epilogue: O_t / l -> bf16 -> global (row = one thread, 256 contiguous bytes per head)
     mbar_wait(&s_full[t], n_kv & 1);
     tc_fence_after();
@@ -325,14 +452,34 @@ extern "C" int drb_attention_bf16(const void* q, const void* k, const void* v, i
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, kTileKV, 64);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    configured = true;
+  // fraction of the exponentials computed on the FMA pipe: 5/16 by default (tuned on B200); the
+  // DRB_ATTN_POLY environment variable selects another instantiation for tuning runs only.
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("DRB_ATTN_POLY");
+    variant = e ? atoi(e) : 2;
+    if (variant < 0 || variant > 3) variant = 2;
+    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x0000u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x1111u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x4924u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x5555u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   }
   AttnParams p{static_cast<__nv_bfloat16*>(o), ld_o, q_len, kv_len};
   dim3 grid((q_len + kTileQ * kQTilesPerCta - 1) / (kTileQ * kQTilesPerCta), num_heads);
-  attention_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (variant) {
+    case 0: attention_kernel<0x0000u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
+    case 1: attention_kernel<0x1111u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
+    case 3: attention_kernel<0x5555u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
+    default: attention_kernel<0x4924u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
+  }
   DRB_CUDA(cudaGetLastError());
   return 0;
 }
+
+#ifdef DRB_ATTN_PROFILE
+using namespace drb;
+extern "C" int drb_debug_attn_profile(unsigned long long* out16) {
+  return drb::check_cuda(cudaMemcpyFromSymbol(out16, g_attn_prof, sizeof(unsigned long long) * 16), "drb_debug_attn_profile");
+}
+#endif

@@ -140,9 +140,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp_idx == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
-    if (is_leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    // The whole warp runs the loop in uniform control flow and one elected lane issues, so that the descriptors
+    // live in uniform registers (what UTCHMMA reads) instead of paying an R2UR round trip per operand.
+    if (is_leader) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN);
+      const bool issuer = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);                   // K-major, LBO field = 1
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);                        // SBO 1024 B, v1, SWIZZLE_128B
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -151,24 +157,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kBlockN;
+        const uint32_t d_tmem = tm + as * kBlockN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_desc_kmajor_sw128(sa);
-          const uint64_t bdesc = make_desc_kmajor_sw128(sa + Cfg::kABytes);
+          const uint32_t a_lo = smem_lo + stage * (Cfg::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_ss<kCtaGroup>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              umma_ss<kCtaGroup>(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k),
+                                 (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (kb | k) != 0);
+            }
+            if constexpr (kCtaGroup == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_pair(&empty_bar[stage], 0x3);
           }
-          if constexpr (kCtaGroup == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_pair(&empty_bar[stage], 0x3);
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if constexpr (kCtaGroup == 1) umma_commit(&tmem_full_bar[as]);
-        else umma_commit_pair(&tmem_full_bar[as], 0x3);
+        if (issuer) {
+          if constexpr (kCtaGroup == 1) umma_commit(&tmem_full_bar[as]);
+          else umma_commit_pair(&tmem_full_bar[as], 0x3);
+        }
+        __syncwarp();
       }
     }
   } else if (warp_idx >= 4) {
