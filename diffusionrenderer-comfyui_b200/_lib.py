@@ -4,13 +4,24 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DRB200_LIB", os.path.join(HERE, "libdrb200.so"))   # override: tuning builds only
 
 DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_UNSUPPORTED = 0, -1, -2, -3
 EPI_STORE, EPI_GELU, EPI_GATED_RESIDUAL = 0, 1, 2
+TMODE_CAUSAL, TMODE_DOWN2, TMODE_UP2 = 0, 1, 2
+RES_NONE, RES_SAME, RES_FRAME_UP2, RES_POOL_HW, RES_POOL_T, RES_NEAREST_UP_HW = 0, 1, 2, 3, 4, 5
+
+
+class Conv3dArgs(Structure):
+    """drb_conv3d_args of include/drb200.h"""
+    _fields_ = [("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("resid", c_void_p),
+                ("stats", c_void_p)] + [(n, c_int) for n in (
+                    "T_in", "H_in", "W_in", "Cin", "T_out", "H_out", "W_out", "Cout", "kt", "kh", "kw", "pad_h", "pad_w",
+                    "stride_hw", "tmode", "out_scale", "out_off_h", "out_off_w", "resid_mode", "resid_H", "resid_W")]
+
 
 # name -> argtypes, in the order of include/drb200.h (tests check that every one is exported)
 PROTOTYPES = {
@@ -30,6 +41,16 @@ PROTOTYPES = {
     "drb_edm_scale_input": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     "drb_edm_euler_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     "drb_postprocess_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "drb_conv3d_cl": [POINTER(Conv3dArgs), c_void_p],
+    "drb_haar_patch": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "drb_haar_unpatch": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "drb_frame_stats_cl": [c_void_p, c_void_p, c_int, c_int64, c_void_p],
+    "drb_groupnorm_apply_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p],
+    "drb_softmax_rows": [c_void_p, c_int64, c_int, c_int, c_float, c_void_p],
+    "drb_transpose_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p],
+    "drb_temporal_attention_cl": [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p],
+    "drb_planar_to_cl": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],
+    "drb_cl_to_planar": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],
 }
 
 _lib = None

@@ -32,8 +32,9 @@ int num_sms();   // multiprocessor count of the current device (cached)
 // 128-byte swizzle (box_cols * 2 must be 128).  Returns 0 or an error code.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
-// 4-D bf16 channels-last activation [T][H][W][C] (C contiguous); box = (bt, bh, bw, bc) with bc*2 == 128.
-int make_tmap_4d_bf16(CUtensorMap* out, const void* base, uint64_t T, uint64_t H, uint64_t W, uint64_t C,
-                      uint32_t bt, uint32_t bh, uint32_t bw, uint32_t bc);
+// rank-`rank` (2..5) bf16 tensor, innermost dimension first: dims[rank] in elements, strides[rank-1] in bytes (dimension 0
+// is contiguous), box[rank] in elements with box[0]*2 == 128; 128-byte swizzle, out-of-bounds elements read as zero.
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box);
 
 }  // namespace drb

@@ -1,0 +1,405 @@
+// drb_conv3d_cl — the tokenizer's causal 3-D convolutions as an implicit GEMM on tcgen05 tensor cores.
+//
+// Replaces CosmosCausalConv3d of diffusers.AutoencoderKLCosmos (the arithmetic behind CleanVAE.py:50-51,59-60; SURVEY.md
+// Appendix B): factorised (1,3,3) spatial and (3,1,1) causal temporal convolutions, 1x1x1 projections, the strided
+// convolutions of the down-sampler and the nearest-neighbour-upsample + (1,3,3) convolution of the up-sampler.
+// Activations are channels-last per frame, [T][H][W][C] bf16; weights [Cout][kt][kh][kw][Cin] bf16.
+//
+// out[t, oh, ow, :] = bias + residual + sum over taps (dt,dy,dx) of W[:, tap, :] . x[tsrc(t,dt), s*h + dy - ph, s*w + dx - pw, :]
+//
+// Implicit GEMM: the M tile is 128 output positions = an 8 x 16 patch (h, w) of one frame; for every tap and every
+// 64-channel chunk the TMA producer loads the *shifted* patch with one 4-D box (c, w, h, t) — out-of-bounds rows and
+// columns arrive as zeros, which IS the spatial zero padding (the halo is never materialised: each tap is its own box
+// served from L2), and the causal replicate-first-frame padding is a clamp of the frame coordinate.  Spatial stride 2
+// uses four tensor maps, one per (row, column) parity of the source, so every tap is still a dense box.  The smem tile
+// has exactly the K-major SWIZZLE_128B layout of the GEMM's A operand, so the rest is gemm.cu's pipeline (1-CTA
+// flavour: tile 128 x N, N = min(256, Cout) chosen at run time, 4-stage ring, two TMEM accumulator stages,
+// warp-uniform MMA issue).
+//
+// Sub-pixel form of "nearest x2 upsample then conv (1,3,3) pad 1" (CosmosUpsample3d): output pixels of parity (py, px)
+// are a 2x2 convolution of the *source-resolution* tensor with pre-summed weights, so the kernel iterates source
+// positions (h, w) and stores to (2h + py, 2w + px) (`out_scale` = 2): 16 tap-GEMMs on quarter-size tiles instead of
+// 9 on full size, and the 4x larger upsampled tensor is never written.
+//
+// Epilogue: + bias, optional residual (same position / frame-mapped / 2x2 or 2-frame average pool / nearest-upsampled
+// source = the "+ avg_pool" and "+ x" terms of the resamplers and the resnet / attention skip), bf16 store, and
+// per-frame sum / sum-of-squares of the stored values accumulated for the per-frame GroupNorm that follows.
+//
+// Roofline: tensor pipe, 2 * T*H*W * Cout * taps*Cin flop per launch.
+#include "../../include/drb200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace drb {
+namespace {
+
+constexpr int kTileH = 8, kTileW = 16;          // 128 output positions per M tile
+constexpr int kMaxN = 256, kBlockK = 64, kUmmaK = 16;
+constexpr int kABytes = 128 * kBlockK * 2;      // 16 KB
+constexpr int kBBytes = kMaxN * kBlockK * 2;    // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kStages = 4;
+constexpr int kConvSmem = kStages * kStageBytes + 1024 + 256;
+constexpr int kConvThreads = 256;
+
+struct ConvMaps {
+  CUtensorMap x[4];   // [0] for stride 1; [py*2 + px] parity views for stride 2
+  CUtensorMap w;
+};
+
+struct ConvParams {
+  int T_out, H_out, W_out;      // positions iterated (tile space)
+  int out_H, out_W;             // dims of the output tensor (= H_out*out_scale when out_scale == 2)
+  int Cin, Cout, block_n;
+  int kt, kh, kw, pad_h, pad_w, stride_hw, tmode;
+  int out_scale, out_off_h, out_off_w;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* resid;
+  int resid_mode;
+  int rH, rW;                   // dims of the residual source tensor (channels = Cout)
+  double* stats;                // [T_out][2] (sum, sum of squares) or null
+};
+
+// source frame of output frame t for temporal tap dt (kt taps)
+__device__ __forceinline__ int src_frame(int tmode, int t, int dt, int kt) {
+  if (tmode == DRB_TMODE_DOWN2) return max(2 * t + dt - 2, 0);               // cat[x0, x], causal pad 1, stride 2
+  if (tmode == DRB_TMODE_UP2) return (max(t + dt - (kt - 1), 0) + 1) >> 1;   // source is repeat_interleave(x, 2)[1:]
+  return max(t + dt - (kt - 1), 0);                                          // causal: first frame replicated in front
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_w = (p.W_out + kTileW - 1) / kTileW, tiles_h = (p.H_out + kTileH - 1) / kTileH;
+  const int tiles_n = (p.Cout + p.block_n - 1) / p.block_n;
+  const int tiles_m = p.T_out * tiles_h * tiles_w;
+  const int num_tiles = tiles_m * tiles_n;
+  const int cchunks = p.Cin / kBlockK;
+  const int taps = p.kt * p.kh * p.kw;
+  const int num_kb = taps * cchunks;
+
+  if (warp_idx == 0 && lane == 0) {
+    prefetch_tmap(&maps.x[0]);
+    prefetch_tmap(&maps.w);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // n-tile fastest: the CTAs working on one spatial tile at the same time share its activation boxes in L2
+  auto decode_tile = [&](int tile, int& t, int& h0, int& w0, int& n0) {
+    const int tn = tile % tiles_n;
+    int m = tile / tiles_n;
+    const int tw = m % tiles_w;
+    m /= tiles_w;
+    const int th = m % tiles_h;
+    t = m / tiles_h;
+    h0 = th * kTileH;
+    w0 = tw * kTileW;
+    n0 = tn * p.block_n;
+  };
+
+  if (warp_idx == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = kABytes + p.block_n * kBlockK * 2;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int t, h0, w0, n0;
+        decode_tile(tile, t, h0, w0, n0);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dx = tap % p.kw, dy = (tap / p.kw) % p.kh, dt = tap / (p.kw * p.kh);
+          const int ts = src_frame(p.tmode, t, dt, p.kt);
+          int hs, wsrc, mi = 0;
+          if (p.stride_hw == 1) {
+            hs = h0 + dy - p.pad_h;
+            wsrc = w0 + dx - p.pad_w;
+          } else {   // source row 2h + r, r = dy - pad: parity view (r & 1), row h + (r - parity) / 2
+            const int ry = dy - p.pad_h, rx = dx - p.pad_w;
+            const int py = ry & 1, px = rx & 1;
+            hs = h0 + ((ry - py) >> 1);
+            wsrc = w0 + ((rx - px) >> 1);
+            mi = py * 2 + px;
+          }
+          for (int cc = 0; cc < cchunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_4d(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
+            tma_load_2d(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK, n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane)
+    const uint32_t idesc = make_idesc_bf16(128, p.block_n);
+    constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const bool issuer = elect_one();
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);
+    int stage = 0, iter = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      mbar_wait(&tmem_empty_bar[as], ((iter >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tm + as * kMaxN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_lo = smem_lo + stage * (kStageBytes >> 4);
+        const uint32_t b_lo = a_lo + (kABytes >> 4);
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_ss<1>(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k),
+                       (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (issuer) umma_commit(&tmem_full_bar[as]);
+      __syncwarp();
+    }
+  } else if (warp_idx >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp_idx - 4;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      int t, h0, w0, n0;
+      decode_tile(tile, t, h0, w0, n0);
+      const int as = iter & 1;
+      mbar_wait(&tmem_full_bar[as], (iter >> 1) & 1);
+      tc_fence_after();
+      const int r = q * 32 + lane;
+      const int h = h0 + r / kTileW, w = w0 + r % kTileW;
+      const bool ok = h < p.H_out && w < p.W_out;
+      const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
+      const int64_t pix = (static_cast<int64_t>(t) * p.out_H + oh) * p.out_W + ow;
+      __nv_bfloat16* orow = p.out + pix * p.Cout;
+      // residual source rows (up to 4 averaged)
+      const __nv_bfloat16* rrow[4] = {nullptr, nullptr, nullptr, nullptr};
+      int nres = 0;
+      float rscale = 1.0f;
+      if (ok) {
+        auto rpix = [&](int tt, int hh, int ww) {
+          return p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout;
+        };
+        if (p.resid_mode == DRB_RES_SAME) {
+          rrow[0] = rpix(t, oh, ow);
+          nres = 1;
+        } else if (p.resid_mode == DRB_RES_FRAME_UP2) {      // x'[t] = x[(t + 1) / 2]
+          rrow[0] = rpix((t + 1) >> 1, oh, ow);
+          nres = 1;
+        } else if (p.resid_mode == DRB_RES_NEAREST_UP_HW) {  // x''[oh, ow] = x'[oh / 2, ow / 2]
+          rrow[0] = rpix(t, oh >> 1, ow >> 1);
+          nres = 1;
+        } else if (p.resid_mode == DRB_RES_POOL_HW) {        // 2x2 average of the zero-padded source
+          nres = 4;
+          rscale = 0.25f;
+          for (int i = 0; i < 4; ++i) {
+            const int hh = 2 * oh + (i >> 1), ww = 2 * ow + (i & 1);
+            rrow[i] = (hh < p.rH && ww < p.rW) ? rpix(t, hh, ww) : nullptr;
+          }
+        } else if (p.resid_mode == DRB_RES_POOL_T) {         // frames max(2t-1, 0) and 2t of the source (cat[x0, x] pooled)
+          nres = 2;
+          rscale = 0.5f;
+          rrow[0] = rpix(max(2 * t - 1, 0), oh, ow);
+          rrow[1] = rpix(2 * t, oh, ow);
+        }
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kMaxN;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kMaxN / 32; ++c) {
+        const int col = n0 + c * 32;
+        if (c * 32 >= p.block_n || col >= p.Cout) break;   // warp-uniform
+        uint32_t acc[32];
+        tmem_ld32(taddr + c * 32, acc);
+        tmem_wait_ld();
+        if (!ok) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cg = col + g * 8;
+          if (cg >= p.Cout || c * 32 + g * 8 >= p.block_n) continue;
+          float v[8];
+          const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
+          const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[2 * j] = __uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bb[j]);
+            v[2 * j + 1] = __uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bb[j]);
+          }
+          if (nres > 0) {
+            float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i >= nres || rrow[i] == nullptr) continue;
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow[i] + cg);
+              const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ra[2 * j] += bf16_lo(rr[j]);
+                ra[2 * j + 1] += bf16_hi(rr[j]);
+              }
+            }
+            // the reference rounds the convolution output to bf16 before adding the skip term
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]) + bf16_round(ra[j] * rscale);
+          }
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
+            s1 += a + b;
+            s2 += a * a + b * b;
+          }
+          *reinterpret_cast<uint4*>(orow + cg) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (p.stats != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+          atomicAdd(&p.stats[2 * t], static_cast<double>(s1));
+          atomicAdd(&p.stats[2 * t + 1], static_cast<double>(s2));
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace
+}  // namespace drb
+
+extern "C" int drb_conv3d_cl(const drb_conv3d_args* a, void* stream) {
+  using namespace drb;
+  DRB_REQUIRE(a != nullptr, "null argument block");
+  DRB_REQUIRE(a->x && a->w && a->bias && a->out, "null pointer");
+  DRB_REQUIRE(a->T_in > 0 && a->H_in > 0 && a->W_in > 0 && a->T_out > 0 && a->H_out > 0 && a->W_out > 0, "bad tensor dims");
+  DRB_REQUIRE(a->Cin > 0 && a->Cin % 64 == 0, "Cin must be a multiple of 64 (zero-pad narrower tensors)");
+  DRB_REQUIRE(a->Cout > 0 && a->Cout % 16 == 0, "Cout must be a multiple of 16");
+  DRB_REQUIRE(a->kt >= 1 && a->kt <= 3 && a->kh >= 1 && a->kh <= 3 && a->kw >= 1 && a->kw <= 3, "taps must be 1..3 per axis");
+  DRB_REQUIRE(a->stride_hw == 1 || a->stride_hw == 2, "spatial stride must be 1 or 2");
+  DRB_REQUIRE(a->pad_h >= 0 && a->pad_h <= 2 && a->pad_w >= 0 && a->pad_w <= 2, "bad padding");
+  DRB_REQUIRE(a->tmode >= DRB_TMODE_CAUSAL && a->tmode <= DRB_TMODE_UP2, "unknown tmode");
+  DRB_REQUIRE(a->resid_mode >= DRB_RES_NONE && a->resid_mode <= DRB_RES_NEAREST_UP_HW, "unknown resid_mode");
+  DRB_REQUIRE((a->resid_mode == DRB_RES_NONE) == (a->resid == nullptr), "resid pointer and resid_mode disagree");
+  DRB_REQUIRE(a->out_scale == 1 || a->out_scale == 2, "out_scale must be 1 or 2");
+  DRB_REQUIRE(a->out_off_h >= 0 && a->out_off_h < a->out_scale && a->out_off_w >= 0 && a->out_off_w < a->out_scale, "bad output offset");
+  DRB_REQUIRE(a->out_scale == 1 || a->stride_hw == 1, "out_scale 2 requires stride 1");
+  DRB_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0,
+              "out / bias / resid must be 16-byte aligned");
+  // temporal extent the frame mapping may touch
+  {
+    const int t_last = a->T_out - 1;
+    int need;
+    if (a->tmode == DRB_TMODE_DOWN2) need = (a->kt == 1) ? 2 * t_last - 2 : 2 * t_last;
+    else if (a->tmode == DRB_TMODE_UP2) need = (t_last + 1) >> 1;
+    else need = t_last;
+    if (need < 0) need = 0;
+    DRB_REQUIRE(need < a->T_in, "temporal mapping reads past the last source frame");
+  }
+  const uint64_t C = static_cast<uint64_t>(a->Cin), W = static_cast<uint64_t>(a->W_in), H = static_cast<uint64_t>(a->H_in),
+                 T = static_cast<uint64_t>(a->T_in);
+  ConvMaps maps;
+  int rc;
+  const uint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+  if (a->stride_hw == 1) {
+    const uint64_t dims[4] = {C, W, H, T};
+    const uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    rc = make_tmap_nd_bf16(&maps.x[0], a->x, 4, dims, strides, box);
+    if (rc) return rc;
+    for (int i = 1; i < 4; ++i) maps.x[i] = maps.x[0];
+  } else {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const uint64_t wp = (W + 1 - px) / 2, hp = (H + 1 - py) / 2;   // ceil((W - px) / 2)
+        CUtensorMap* m = &maps.x[py * 2 + px];
+        if (wp == 0 || hp == 0) {       // no source pixel of this parity (H or W == 1): never selected by a valid tap
+          *m = maps.x[0];
+          continue;
+        }
+        const uint64_t dims[4] = {C, wp, hp, T};
+        const uint64_t strides[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
+        const char* base = static_cast<const char*>(a->x) + (static_cast<uint64_t>(py) * W + px) * C * 2;
+        rc = make_tmap_nd_bf16(m, base, 4, dims, strides, box);
+        if (rc) return rc;
+      }
+  }
+  const int taps = a->kt * a->kh * a->kw;
+  const int block_n = a->Cout <= kMaxN ? a->Cout : kMaxN;
+  rc = make_tmap_2d_bf16(&maps.w, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cin, static_cast<uint64_t>(taps) * a->Cin,
+                         block_n, kBlockK);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    DRB_CUDA(cudaFuncSetAttribute(conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+    configured = true;
+  }
+  ConvParams p{};
+  p.T_out = a->T_out; p.H_out = a->H_out; p.W_out = a->W_out;
+  p.out_H = a->H_out * a->out_scale; p.out_W = a->W_out * a->out_scale;
+  p.Cin = a->Cin; p.Cout = a->Cout; p.block_n = block_n;
+  p.kt = a->kt; p.kh = a->kh; p.kw = a->kw; p.pad_h = a->pad_h; p.pad_w = a->pad_w; p.stride_hw = a->stride_hw; p.tmode = a->tmode;
+  p.out_scale = a->out_scale; p.out_off_h = a->out_off_h; p.out_off_w = a->out_off_w;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.bias = static_cast<const __nv_bfloat16*>(a->bias);
+  p.resid = static_cast<const __nv_bfloat16*>(a->resid);
+  p.resid_mode = a->resid_mode;
+  p.rH = a->resid_H; p.rW = a->resid_W;
+  p.stats = a->stats;
+  const int tiles = a->T_out * ((a->H_out + kTileH - 1) / kTileH) * ((a->W_out + kTileW - 1) / kTileW) *
+                    ((a->Cout + block_n - 1) / block_n);
+  int grid = num_sms();
+  if (grid > tiles) grid = tiles;
+  conv3d_kernel<<<grid, kConvThreads, kConvSmem, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  DRB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -75,25 +75,34 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
-int make_tmap_4d_bf16(CUtensorMap* out, const void* base, uint64_t T, uint64_t H, uint64_t W, uint64_t C,
-                      uint32_t bt, uint32_t bh, uint32_t bw, uint32_t bc) {
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box) {
   auto fn = encode_fn();
   if (!fn) {
     g_last_error = "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)";
     return DRB_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("make_tmap_4d_bf16", "base pointer not 16-byte aligned");
-  if ((C * 2) % 16 != 0) return fail("make_tmap_4d_bf16", "channel count must be a multiple of 8");
-  if (bc * 2 != 128) return fail("make_tmap_4d_bf16", "box must cover 64 channels (128 bytes)");
-  cuuint64_t dims[4] = {C, W, H, T};
-  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {bc, bw, bh, bt};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  if (rank < 2 || rank > 5) return fail("make_tmap_nd_bf16", "rank must be 2..5");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("make_tmap_nd_bf16", "base pointer not 16-byte aligned");
+  if (box[0] * 2 != 128) return fail("make_tmap_nd_bf16", "box must cover 64 innermost elements (128 bytes)");
+  cuuint64_t d[5];
+  cuuint64_t st[4];
+  cuuint32_t b[5];
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    if (dims[i] == 0 || box[i] == 0 || box[i] > 256) return fail("make_tmap_nd_bf16", "bad dimension or box");
+    d[i] = dims[i];
+    b[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides[i] % 16 != 0) return fail("make_tmap_nd_bf16", "strides must be multiples of 16 bytes");
+    st[i] = strides[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, st, b, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    g_last_error = "cuTensorMapEncodeTiled(4d) failed with CUresult " + std::to_string(static_cast<int>(r));
+    g_last_error = "cuTensorMapEncodeTiled(nd) failed with CUresult " + std::to_string(static_cast<int>(r));
     return DRB_ERR_CUDA;
   }
   return 0;

@@ -127,6 +127,8 @@ class CleanDiffusionRendererModel(nn.Module):
             raise RuntimeError("VAE not initialized in model.")
         if x.ndim != 5:
             raise ValueError(f"Model encode expects a 5D tensor (B,C,T,H,W), but got {x.ndim}D.")
+        if hasattr(self.vae, "encode_scaled"):     # B200 tokenizer: the sigma_data factor rides on its output layout kernel
+            return self.vae.encode_scaled(x, self.scheduler.sigma_data)
         return self.vae.encode(x) * self.scheduler.sigma_data
 
     def decode(self, x: Tensor) -> Tensor:
@@ -134,6 +136,8 @@ class CleanDiffusionRendererModel(nn.Module):
             raise RuntimeError("VAE not initialized in model.")
         if x.ndim != 5:
             raise ValueError(f"Model decode expects a 5D latent (B,C,T,H,W), but got {x.ndim}D.")
+        if hasattr(self.vae, "decode_scaled"):
+            return self.vae.decode_scaled(x, 1.0 / self.scheduler.sigma_data)
         return self.vae.decode(x / self.scheduler.sigma_data)
 
     # ---------------------------------------------------------------- conditions (reference :158-209)

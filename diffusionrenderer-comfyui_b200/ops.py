@@ -181,3 +181,138 @@ def postprocess_u8(video: torch.Tensor, normalize_normal: bool = False) -> torch
     out = torch.empty((T, H, W, 3), device=video.device, dtype=torch.uint8)
     _lib.call("drb_postprocess_u8", video.data_ptr(), out.data_ptr(), T, H, W, int(bool(normalize_normal)), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ tokenizer operators
+def _req_cl(t: torch.Tensor, name: str) -> None:
+    _req(t, name)
+    if t.ndim != 4 or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous channels-last activation [T, H, W, C]")
+
+
+def conv3d_cl(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, pad_h: int = 0, pad_w: int = 0, stride_hw: int = 1,
+              tmode: int = _lib.TMODE_CAUSAL, out_thw: Optional[tuple] = None, resid: Optional[torch.Tensor] = None,
+              resid_mode: int = _lib.RES_NONE, stats: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              out_scale: int = 1, out_off: tuple = (0, 0)) -> torch.Tensor:
+    """x [T,H,W,Cin], w [Cout,kt,kh,kw,Cin], bias [Cout] -> out [T_out, H_out*out_scale, W_out*out_scale, Cout].
+    `out_thw` = positions iterated (default: same as the input); `stats` float64 [T_out,2] is accumulated into."""
+    _req_cl(x, "x"), _req(w, "w"), _req(bias, "bias")
+    if w.ndim != 5 or not w.is_contiguous() or w.shape[4] != x.shape[3]:
+        raise ValueError(f"w must be contiguous [Cout, kt, kh, kw, Cin={x.shape[3]}], got {tuple(w.shape)}")
+    T, H, W, Cin = x.shape
+    Cout, kt, kh, kw, _ = w.shape
+    To, Ho, Wo = out_thw if out_thw is not None else (T, H, W)
+    if out is None:
+        out = torch.empty((To, Ho * out_scale, Wo * out_scale, Cout), device=x.device, dtype=BF16)
+    _req_cl(out, "out")
+    if tuple(out.shape) != (To, Ho * out_scale, Wo * out_scale, Cout):
+        raise ValueError("out has the wrong shape")
+    a = _lib.Conv3dArgs()
+    a.x, a.w, a.bias, a.out = x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
+    a.resid, a.stats = None, None
+    a.resid_H = a.resid_W = 0
+    if resid is not None:
+        _req_cl(resid, "resid")
+        if resid.shape[3] != Cout:
+            raise ValueError("resid must have Cout channels")
+        a.resid, a.resid_H, a.resid_W = resid.data_ptr(), resid.shape[1], resid.shape[2]
+    if stats is not None:
+        _req(stats, "stats", torch.float64)
+        if tuple(stats.shape) != (To, 2):
+            raise ValueError("stats must be float64 [T_out, 2]")
+        a.stats = stats.data_ptr()
+    a.T_in, a.H_in, a.W_in, a.Cin = T, H, W, Cin
+    a.T_out, a.H_out, a.W_out, a.Cout = To, Ho, Wo, Cout
+    a.kt, a.kh, a.kw, a.pad_h, a.pad_w, a.stride_hw, a.tmode = kt, kh, kw, pad_h, pad_w, stride_hw, tmode
+    a.out_scale, a.out_off_h, a.out_off_w = out_scale, out_off[0], out_off[1]
+    a.resid_mode = resid_mode
+    _lib.call("drb_conv3d_cl", a, _stream())
+    return out
+
+
+def haar_patch(x: torch.Tensor) -> torch.Tensor:
+    """x [C,T,H,W] bf16 planar -> [(T+3)//4, H//4, W//4, 64*C] channels-last"""
+    _req(x, "x")
+    if x.ndim != 4 or not x.is_contiguous():
+        raise ValueError("x must be contiguous [C, T, H, W]")
+    C, T, H, W = x.shape
+    out = torch.empty(((T + 3) // 4, H // 4, W // 4, 64 * C), device=x.device, dtype=BF16)
+    _lib.call("drb_haar_patch", x.data_ptr(), out.data_ptr(), C, T, H, W, _stream())
+    return out
+
+
+def haar_unpatch(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[Tp,Hp,Wp,64*C] channels-last -> [C, 4*Tp-3, 4*Hp, 4*Wp] planar"""
+    _req_cl(x, "x")
+    Tp, Hp, Wp, CC = x.shape
+    if CC % 64:
+        raise ValueError("channel count must be 64 * C")
+    C = CC // 64
+    if out is None:
+        out = torch.empty((C, 4 * Tp - 3, 4 * Hp, 4 * Wp), device=x.device, dtype=BF16)
+    _lib.call("drb_haar_unpatch", x.data_ptr(), out.data_ptr(), C, Tp, Hp, Wp, _stream())
+    return out
+
+
+def frame_stats(x: torch.Tensor) -> torch.Tensor:
+    _req_cl(x, "x")
+    T = x.shape[0]
+    stats = torch.empty((T, 2), device=x.device, dtype=torch.float64)
+    _lib.call("drb_frame_stats_cl", x.data_ptr(), stats.data_ptr(), T, x[0].numel(), _stream())
+    return stats
+
+
+def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cl(x, "x"), _req(stats, "stats", torch.float64), _req(gamma, "gamma"), _req(beta, "beta")
+    T, H, W, C = x.shape
+    if gamma.numel() != C or beta.numel() != C or tuple(stats.shape) != (T, 2):
+        raise ValueError("gamma/beta/stats do not match x")
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("drb_groupnorm_apply_cl", x.data_ptr(), out.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), T,
+              H * W, C, int(bool(silu)), _stream())
+    return out
+
+
+def softmax_rows(s: torch.Tensor, cols: int, scale: float) -> torch.Tensor:
+    _req(s, "s")
+    _lib.call("drb_softmax_rows", s.data_ptr(), _rows2d(s, "s"), s.shape[0], cols, float(scale), _stream())
+    return s
+
+
+def transpose(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """x [rows, cols] (row-strided ok) -> out [cols, ld_out >= rows]; columns beyond `rows` are zeroed."""
+    _req(x, "x"), _req(out, "out")
+    _lib.call("drb_transpose_bf16", x.data_ptr(), _rows2d(x, "x"), out.data_ptr(), _rows2d(out, "out"), x.shape[0], x.shape[1],
+              _stream())
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cl(qkv, "qkv")
+    T, H, W, C3 = qkv.shape
+    if out is None:
+        out = torch.empty((T, H, W, C3 // 3), device=qkv.device, dtype=BF16)
+    _lib.call("drb_temporal_attention_cl", qkv.data_ptr(), out.data_ptr(), T, H * W, C3 // 3, _stream())
+    return out
+
+
+def planar_to_cl(x: torch.Tensor, c_pad: int, scale: float = 1.0) -> torch.Tensor:
+    """x [C,T,H,W] -> [T,H,W,c_pad]"""
+    _req(x, "x")
+    if x.ndim != 4 or not x.is_contiguous():
+        raise ValueError("x must be contiguous [C, T, H, W]")
+    C, T, H, W = x.shape
+    out = torch.empty((T, H, W, c_pad), device=x.device, dtype=BF16)
+    _lib.call("drb_planar_to_cl", x.data_ptr(), out.data_ptr(), C, c_pad, T * H * W, float(scale), _stream())
+    return out
+
+
+def cl_to_planar(x: torch.Tensor, C: int, scale: float = 1.0) -> torch.Tensor:
+    """x [T,H,W,c_pad] -> [C,T,H,W] (first C channels)"""
+    _req_cl(x, "x")
+    T, H, W, c_pad = x.shape
+    out = torch.empty((C, T, H, W), device=x.device, dtype=BF16)
+    _lib.call("drb_cl_to_planar", x.data_ptr(), out.data_ptr(), C, c_pad, T * H * W, float(scale), _stream())
+    return out

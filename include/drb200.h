@@ -120,6 +120,67 @@ int drb_edm_euler_step(const void* model_output, const void* x, const float* sig
  * (1+v).clamp(0,2)/2*255 -> uint8 (truncating), BCTHW -> BTHWC.  video: bf16 [3,T,H,W]; out: uint8 [T,H,W,3]. */
 int drb_postprocess_u8(const void* video, void* out_u8, int T, int H, int W, int normalize_normal, void* stream);
 
+/* ==== CV8x8x8 causal video tokenizer ===========================================================================
+ * The reference only wraps diffusers.AutoencoderKLCosmos (CleanVAE.py:3,18,50-51,59-60); the entry points below are the
+ * operators of that class.  Inside the tokenizer activations are channels-last per frame,
+ * bf16 [T][H][W][C]; pixel-space clips and latents at its boundary are planar bf16 [C][T][H][W] (BCTHW, B = 1). */
+
+/* temporal source-frame mapping of a convolution (kt taps, output frame t, tap dt) */
+#define DRB_TMODE_CAUSAL 0 /* src = max(t + dt - (kt-1), 0): first frame replicated in front (CosmosCausalConv3d)        */
+#define DRB_TMODE_DOWN2 1  /* src = max(2t + dt - 2, 0): cat[x0, x] then causal conv with temporal stride 2 (Downsample) */
+#define DRB_TMODE_UP2 2    /* src = (max(t + dt - (kt-1), 0) + 1) / 2: causal conv of repeat_interleave(x, 2)[1:] (Upsample) */
+/* residual term added in the epilogue, indexed by the output position (t, oh, ow) */
+#define DRB_RES_NONE 0
+#define DRB_RES_SAME 1          /* resid[t, oh, ow]                               resnet / attention skip               */
+#define DRB_RES_FRAME_UP2 2     /* resid[(t+1)/2, oh, ow]                         "+ x" of the temporal upsample        */
+#define DRB_RES_POOL_HW 3       /* mean of resid[t, 2oh+{0,1}, 2ow+{0,1}] (zero beyond the edge)  "+ avg_pool" spatial  */
+#define DRB_RES_POOL_T 4        /* mean of resid[max(2t-1,0)], resid[2t]          "+ avg_pool" temporal                 */
+#define DRB_RES_NEAREST_UP_HW 5 /* resid[t, oh/2, ow/2]                           "+ x" of the spatial upsample         */
+
+typedef struct drb_conv3d_args {
+  const void* x;     /* bf16 [T_in][H_in][W_in][Cin], Cin % 64 == 0                                                     */
+  const void* w;     /* bf16 [Cout][kt][kh][kw][Cin]                                                                    */
+  const void* bias;  /* bf16 [Cout]                                                                                     */
+  void* out;         /* bf16 [T_out][H_out*out_scale][W_out*out_scale][Cout], Cout % 16 == 0                            */
+  const void* resid; /* bf16 [*][resid_H][resid_W][Cout] or NULL (resid_mode DRB_RES_NONE)                              */
+  double* stats;     /* nullable: [T_out][2] += (sum, sum of squares) of the stored outputs of each frame               */
+  int T_in, H_in, W_in, Cin;
+  int T_out, H_out, W_out, Cout; /* positions iterated: out position (h, w) reads source rows stride_hw*h + dy - pad_h  */
+  int kt, kh, kw, pad_h, pad_w, stride_hw, tmode;
+  int out_scale, out_off_h, out_off_w; /* position (h, w) is stored at (h*out_scale + out_off_h, w*out_scale + out_off_w) */
+  int resid_mode, resid_H, resid_W;
+} drb_conv3d_args;
+
+/* Implicit-GEMM causal 3-D convolution on tcgen05 tensor cores (TMA box per tap; OOB zero fill = spatial padding).
+ * Replaces CosmosCausalConv3d / CosmosConvProjection3d / the convolutions of CosmosDownsample3d and CosmosUpsample3d. */
+int drb_conv3d_cl(const drb_conv3d_args* args, void* stream);
+
+/* CosmosPatchEmbed3d ("haar", patch 4): x bf16 [C][T][H][W] -> out bf16 [(T+3)/4][H/4][W/4][64*C]: first frame repeated
+ * 4x, two levels of 3-D Haar DWT (sub-bands lll,llh,...,hhh time-first, / sqrt(8) per level).  T = 1 + 4k, H,W % 4 == 0. */
+int drb_haar_patch(const void* x, void* out, int C, int T, int H, int W, void* stream);
+/* CosmosUnpatcher3d: in bf16 [Tp][Hp][Wp][64*C] -> out bf16 [C][4*Tp-3][4*Hp][4*Wp] (first 3 frames dropped). */
+int drb_haar_unpatch(const void* in, void* out, int C, int Tp, int Hp, int Wp, void* stream);
+
+/* CosmosCausalGroupNorm(num_groups = 1) = one (mean, var) per frame over H*W*C, eps 1e-6, affine.
+ * drb_frame_stats_cl zeroes and fills stats[T][2] = (sum, sum of squares); drb_conv3d_cl accumulates the same in its
+ * epilogue (the caller zeroes).  drb_groupnorm_apply_cl: out = act(bf16(norm(x)*gamma + beta)), act = SiLU if `silu`. */
+int drb_frame_stats_cl(const void* x, double* stats, int T, int64_t per_frame, void* stream);
+int drb_groupnorm_apply_cl(const void* x, void* out, const double* stats, const void* gamma, const void* beta, int T,
+                           int64_t hw, int C, int silu, void* stream);
+
+/* Spatial attention of the mid block (one head of dim C over the H*W tokens of a frame) is scores GEMM -> row softmax
+ * -> P.V GEMM, both GEMMs being drb_gemm_bf16:  s[r, :cols] <- softmax(scale * s[r, :cols]) in place, s[r, cols:ld] <- 0. */
+int drb_softmax_rows(void* s, int64_t ld, int rows, int cols, float scale, void* stream);
+/* out[c][r] = in[r][c] for r < rows, 0 for rows <= r < ld_out (V^T as the K-major operand of the P.V GEMM). */
+int drb_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols, void* stream);
+/* Causal temporal attention (one head of dim C over the T frames of a pixel): qkv bf16 [T][hw][3C] -> out [T][hw][C]. */
+int drb_temporal_attention_cl(const void* qkv, void* out, int T, int64_t hw, int C, void* stream);
+
+/* Boundary layouts: planar [C][thw] <-> channels-last [thw][Cpad] (extra channels zero), values scaled by `scale`
+ * (the sigma_data factor of model_diffusion_renderer.py:146,156 rides along here). */
+int drb_planar_to_cl(const void* x, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
+int drb_cl_to_planar(const void* in, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
