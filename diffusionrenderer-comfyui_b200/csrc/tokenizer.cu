@@ -193,7 +193,8 @@ frame_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ sta
   }
 }
 
-// out = act(bf16((x - mean_t) * rstd_t * gamma[c] + beta[c])), act = SiLU (rounded again) or identity; eps 1e-6.
+// out = act(bf16((x - mean_t) * rstd_t * gamma[c] + beta[c])), act = SiLU (rounded again) or identity; eps 1e-6;
+// mean_t and rstd_t rounded to bf16 (see below).
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const double* __restrict__ stats,
                        const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int64_t per_frame, int C,
@@ -203,7 +204,11 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
   const double mean_d = stats[2 * t] / n;
   double var_d = stats[2 * t + 1] / n - mean_d * mean_d;
   if (var_d < 0.0) var_d = 0.0;
-  const float mean = static_cast<float>(mean_d), rstd = rsqrtf(static_cast<float>(var_d) + 1e-6f);
+  // PyTorch's CUDA GroupNorm keeps the per-group mean and rstd in the *input* dtype when the affine parameters share it
+  // (native/cuda/group_norm_kernel.cu: RowwiseMoments writes T, ComputeFusedParams reads T), so the reference pipeline in
+  // bf16 normalises with bf16-rounded statistics; reproduced here (verified bit-equal on B200, tests/test_tokenizer_gpu.py).
+  const float mean = bf16_round(static_cast<float>(mean_d));
+  const float rstd = bf16_round(rsqrtf(static_cast<float>(var_d) + 1e-6f));
   const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(t) * per_frame);
   uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(t) * per_frame);
   const int64_t n8 = per_frame >> 3;

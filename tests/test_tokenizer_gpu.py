@@ -165,7 +165,7 @@ def test_groupnorm_apply_and_frame_stats(silu):
     ref = cl(ref)
     bad = (got.float() - ref.float()).abs() > 2 ** -6 * ref.float().abs().clamp_min(0.25)
     assert not bad.any()
-    assert (got == ref).float().mean() > 0.9
+    assert (got == ref).float().mean() > 0.97      # incl. torch's bf16-rounded mean / rstd (see tokenizer.cu)
 
 
 def test_softmax_transpose_temporal_attention():

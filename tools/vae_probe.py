@@ -26,17 +26,22 @@ vae.reset_dtype(torch.bfloat16)
 x = (torch.rand(1, 3, T, H, W, device="cuda") * 2 - 1).bfloat16()
 
 
-def timed(fn, n=3):
+def timed(fn, n=int(os.environ.get("PROBE_ITERS", "3"))):
     fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.LAUNCHES
-    e0.record()
-    for _ in range(n):
+    best = 1e9
+    for i in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
         out = fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n, (_lib.LAUNCHES - l0) // n, out
+        e1.record()
+        t_host = (time.perf_counter() - t0) * 1e3
+        torch.cuda.synchronize()
+        print(f"   iter {i}: device {e0.elapsed_time(e1):.1f} ms, host enqueue {t_host:.1f} ms")
+        best = min(best, e0.elapsed_time(e1))
+    return best, (_lib.LAUNCHES - l0) // n, out
 
 
 scale = H * W / (704 * 1280)
