@@ -159,6 +159,7 @@ class CleanGeneralDIT(nn.Module):
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._cp = None     # context_parallel.ContextParallel when one video is split over several GPUs
 
     @torch.no_grad()
     def init_weights_(self, seed: int = 0) -> "CleanGeneralDIT":
@@ -241,9 +242,19 @@ class CleanGeneralDIT(nn.Module):
         self._ws.clear()
         return P
 
-    def _workspace(self, T: int, H: int, W: int, dev) -> Dict[str, torch.Tensor]:
-        """Activation buffers for one clip shape (allocated once, reused every forward)."""
-        key = (T, H, W, dev)
+    def enable_context_parallel(self, cp) -> None:
+        """Split every forward's token sequence over the ranks of `cp` (context_parallel.ContextParallel, or None to go
+        back to one GPU).  All ranks then call forward / the sampler with identical arguments and get identical results."""
+        if cp is not None and self.num_heads % cp.world:
+            raise ValueError(f"{self.num_heads} heads do not split over {cp.world} ranks")
+        self._cp = cp
+        self._ws.clear()
+
+    def _workspace(self, T: int, H: int, W: int, dev, cp=None) -> Dict[str, torch.Tensor]:
+        """Activation buffers for one clip shape (allocated once, reused every forward).  With `cp`, T counts the latent
+        frames of THIS rank: token buffers hold the local S/P tokens, `a2a` [S, 3D/P] receives this rank's heads of every
+        token, and `attn` / `a2a` are peer-mapped so that the other ranks' kernels store into them directly."""
+        key = (T, H, W, dev, id(cp))
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -251,13 +262,21 @@ class CleanGeneralDIT(nn.Module):
         S = T * (H // 2) * (W // 2)
         new = lambda *s, dtype=BF16: torch.empty(*s, device=dev, dtype=dtype)
         kpad = self._packed["wx"].shape[1]
-        cos, sin = self.pos_embedder.tables(T, H // 2, W // 2, BF16)
+        world, rank = (cp.world, cp.rank) if cp is not None else (1, 0)
+        cos, sin = self.pos_embedder.tables(T * world, H // 2, W // 2, BF16)
+        cos, sin = cos[rank * S:(rank + 1) * S].contiguous(), sin[rank * S:(rank + 1) * S].contiguous()
         ws = {
             "S": S, "tok": torch.zeros(S, kpad, device=dev, dtype=BF16), "x": new(S, D), "xm": new(S, D), "qkv": new(S, 3 * D),
-            "attn": new(S, D), "h": new(S, self.hidden), "y": new(S, self.out_patch_dim), "cos": cos, "sin": sin,
+            "h": new(S, self.hidden), "y": new(S, self.out_patch_dim), "cos": cos, "sin": sin,
             "e": new(D), "emb": new(D), "t1": new(D), "lora": new(3 * D), "mod_h": new(3 * L + 1, self.adaln_lora_dim),
             "mod": new(3 * L + 1, 3 * D), "ca_tmp": new(L, D), "ca_vec": new(L, D), "sigma": new(1, dtype=torch.float32),
+            "cp": cp,
         }
+        if cp is None:
+            ws["attn"] = new(S, D)
+        else:
+            ws["attn"], ws["attn_ptrs"] = cp.alloc("attn", (S, D))
+            ws["a2a"], ws["a2a_ptrs"] = cp.alloc("a2a", (S * world, 3 * D // world))
         self._ws = {key: ws}   # one live shape at a time: the buffers are large (MLP hidden = 0.92 GB at 57x704x1280)
         return ws
 
@@ -293,36 +312,73 @@ class CleanGeneralDIT(nn.Module):
         ops.gemv_batched(P["mod_a"], ws["emb"], ws["mod_h"], act=1)
         ops.gemv_batched(P["mod_b"], ws["mod_h"], ws["mod"], add=ws["lora"])
 
+    def stage_embed(self, ws) -> None:
+        ops.gemm(ws["tok"], self._packed["wx"], out=ws["x"])
+
+    def stage_pre_attention(self, ws, i: int) -> None:
+        """AdaLN -> fused QKV GEMM -> per-head RMSNorm + RoPE (under context parallelism: stored to the head owners)"""
+        P, D, Hh, cp = self._packed, self.model_channels, self.num_heads, ws["cp"]
+        m_sa = ws["mod"][3 * i]
+        ops.adaln_modulate(ws["x"], m_sa[:D], m_sa[D:2 * D], out=ws["xm"])
+        ops.gemm(ws["xm"], P["qkv"][i], out=ws["qkv"])
+        if cp is None:
+            ops.qk_norm_rope(ws["qkv"], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], Hh)
+        else:
+            ops.qk_norm_rope_scatter(ws["qkv"], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], Hh, ws["a2a_ptrs"],
+                                     3 * D // cp.world, cp.rank * ws["S"])
+
+    def stage_attention(self, ws, i: int, timers: Optional[list] = None) -> None:
+        D, Hh, cp = self.model_channels, self.num_heads, ws["cp"]
+        if timers is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        if cp is None:
+            qkv = ws["qkv"]
+            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Hh, out=ws["attn"])
+        else:
+            Dp, a2a = D // cp.world, ws["a2a"]
+            ops.attention_cp(a2a[:, :Dp], a2a[:, Dp:2 * Dp], a2a[:, 2 * Dp:], Hh // cp.world, ws["attn_ptrs"], D, ws["S"],
+                             cp.rank * Dp)
+        if timers is not None:
+            ev[1].record()
+            timers.append(ev)
+
+    def stage_post_attention(self, ws, i: int, use_ca: bool) -> None:
+        """out-projection with gated residual; cross-attention vector + AdaLN; MLP with gated residual"""
+        P, D = self._packed, self.model_channels
+        x, xm, h, mod = ws["x"], ws["xm"], ws["h"], ws["mod"]
+        m_sa, m_ca, m_mlp = mod[3 * i], mod[3 * i + 1], mod[3 * i + 2]
+        ops.gemm(ws["attn"], P["wo"][i], out=x, epilogue=_lib.EPI_GATED_RESIDUAL, resid=x, gate=m_sa[2 * D:])
+        if use_ca:
+            ops.adaln_modulate(x, m_mlp[:D], m_mlp[D:2 * D], out=xm, add_gate=m_ca[2 * D:], add_vec=ws["ca_vec"][i])
+        else:
+            ops.adaln_modulate(x, m_mlp[:D], m_mlp[D:2 * D], out=xm)
+        ops.gemm(xm, P["w1"][i], out=h, epilogue=_lib.EPI_GELU)
+        ops.gemm(h, P["w2"][i], out=x, epilogue=_lib.EPI_GATED_RESIDUAL, resid=x, gate=m_mlp[2 * D:])
+
+    def stage_final(self, ws) -> torch.Tensor:
+        D = self.model_channels
+        m_f = ws["mod"][3 * self.num_blocks]
+        ops.adaln_modulate(ws["x"], m_f[:D], m_f[D:2 * D], out=ws["xm"])
+        ops.gemm(ws["xm"], self.final_layer.linear.weight, out=ws["y"])
+        return ws["y"]
+
     def run_blocks(self, ws, use_ca: bool, timers: Optional[list] = None) -> torch.Tensor:
         """tokens -> y [S, 64].  Consumes ws['tok'] / ws['mod'] / ws['ca_vec'].
-        `timers` (bench only): a list that receives one (start, end) CUDA-event pair per attention launch."""
-        P, D, L, Hh = self._packed, self.model_channels, self.num_blocks, self.num_heads
-        x, xm, qkv, attn, h, mod = ws["x"], ws["xm"], ws["qkv"], ws["attn"], ws["h"], ws["mod"]
-        ops.gemm(ws["tok"], P["wx"], out=x)
-        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
-        for i in range(L):
-            m_sa, m_ca, m_mlp = mod[3 * i], mod[3 * i + 1], mod[3 * i + 2]
-            ops.adaln_modulate(x, m_sa[:D], m_sa[D:2 * D], out=xm)
-            ops.gemm(xm, P["qkv"][i], out=qkv)
-            ops.qk_norm_rope(qkv, P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], Hh)
-            if timers is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            ops.attention(q, k, v, Hh, out=attn)
-            if timers is not None:
-                ev[1].record()
-                timers.append(ev)
-            ops.gemm(attn, P["wo"][i], out=x, epilogue=_lib.EPI_GATED_RESIDUAL, resid=x, gate=m_sa[2 * D:])
-            if use_ca:
-                ops.adaln_modulate(x, m_mlp[:D], m_mlp[D:2 * D], out=xm, add_gate=m_ca[2 * D:], add_vec=ws["ca_vec"][i])
-            else:
-                ops.adaln_modulate(x, m_mlp[:D], m_mlp[D:2 * D], out=xm)
-            ops.gemm(xm, P["w1"][i], out=h, epilogue=_lib.EPI_GELU)
-            ops.gemm(h, P["w2"][i], out=x, epilogue=_lib.EPI_GATED_RESIDUAL, resid=x, gate=m_mlp[2 * D:])
-        m_f = mod[3 * L]
-        ops.adaln_modulate(x, m_f[:D], m_f[D:2 * D], out=xm)
-        ops.gemm(xm, self.final_layer.linear.weight, out=ws["y"])
-        return ws["y"]
+        `timers` (bench only): a list that receives one (start, end) CUDA-event pair per attention launch.
+        Under context parallelism the two device-side barriers per block order the P2P stores of the fused exchange:
+        q/k/v rows must have landed before the attention reads them, its output rows before the out-projection."""
+        cp = ws["cp"]
+        self.stage_embed(ws)
+        for i in range(self.num_blocks):
+            self.stage_pre_attention(ws, i)
+            if cp is not None:
+                cp.barrier()
+            self.stage_attention(ws, i, timers)
+            if cp is not None:
+                cp.barrier()
+            self.stage_post_attention(ws, i, use_ca)
+        return self.stage_final(ws)
 
     def denoise_step(self, ws, x: torch.Tensor, sigma: torch.Tensor, sigma_next: torch.Tensor, use_ca: bool,
                      timers: Optional[list] = None) -> None:
@@ -346,19 +402,32 @@ class CleanGeneralDIT(nn.Module):
         return T, H, W
 
     def forward(self, x, timesteps, crossattn_emb, latent_condition, **kwargs):
-        """reference CleanGeneralDIT.forward (:656-718): x is the c_in-scaled noisy latent; returns F (B,16,T,H,W)."""
+        """reference CleanGeneralDIT.forward (:656-718): x is the c_in-scaled noisy latent; returns F (B,16,T,H,W).
+        With context parallelism enabled every rank passes the same full tensors, computes its frame slice and
+        receives the full F."""
         T, H, W = self._check_input(x)
         self._ensure_packed()
-        ws = self._workspace(T, H, W, x.device)
+        cp = self._cp
+        t0, t1 = (0, T)
+        if cp is not None:
+            from .context_parallel import shard_frames
+            t0, t1 = shard_frames(T, cp.rank, cp.world)
+            x = x[:, :, t0:t1]
+            if latent_condition is not None:
+                latent_condition = latent_condition[:, :, t0:t1]
+        Tl = t1 - t0
+        ws = self._workspace(Tl, H, W, x.device, cp)
         ws["sigma"].copy_(torch.as_tensor(timesteps, dtype=torch.float32).reshape(-1)[:1])
         self.modulation(ws, ws["sigma"])
-        self.prepare_condition(ws, latent_condition, T, H, W)
-        ops.patchify_condition(x.reshape(-1, T, H, W).to(BF16).contiguous(), ws["tok"], 0, T, H, W)
+        self.prepare_condition(ws, latent_condition, Tl, H, W)
+        ops.patchify_condition(x.reshape(-1, Tl, H, W).to(BF16).contiguous(), ws["tok"], 0, Tl, H, W)
         use_ca = self.prepare_context(ws, crossattn_emb)
         y = self.run_blocks(ws, use_ca)
-        out = torch.empty((1, self.out_channels, T, H, W), device=x.device, dtype=BF16)
-        ops.unpatchify_euler(y, None, 0.0, None, None, None, None, f_out=out[0])
-        return out
+        out = torch.empty((self.out_channels, Tl, H, W), device=x.device, dtype=BF16)
+        ops.unpatchify_euler(y, None, 0.0, None, None, None, None, f_out=out)
+        if cp is not None:
+            out = cp.all_gather_frames(out)
+        return out.unsqueeze(0)
 
 
 class CleanDiffusionRendererGeneralDIT(CleanGeneralDIT):

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DRB200_LIB", os.path.join(HERE, "libdrb200.so"))   # override: tuning builds only
@@ -51,7 +51,24 @@ PROTOTYPES = {
     "drb_temporal_attention_cl": [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p],
     "drb_planar_to_cl": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],
     "drb_cl_to_planar": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],
+    "drb_attention_bf16_cp": [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int, c_int,
+                              c_int, c_void_p],
+    "drb_cp_qk_norm_rope_scatter": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p), c_int,
+                                    c_int64, c_int, c_void_p],
+    "drb_cp_barrier": [POINTER(c_void_p), c_int, c_int, c_uint32, c_void_p],
+    "drb_peer_alloc": [c_int64, POINTER(c_void_p)],
+    "drb_peer_free": [c_void_p],
+    "drb_peer_export": [c_void_p, c_void_p],
+    "drb_peer_import": [c_void_p, POINTER(c_void_p)],
+    "drb_peer_close": [c_void_p],
 }
+CP_MAX_RANKS = 8
+PEER_HANDLE_BYTES = 64
+
+
+def ptr_array(ptrs):
+    """ctypes void*[n] from a list of integer device pointers"""
+    return (c_void_p * len(ptrs))(*ptrs)
 
 _lib = None
 

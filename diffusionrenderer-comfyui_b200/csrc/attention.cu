@@ -36,9 +36,12 @@ constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // lo
 constexpr float kRescaleThreshold = 8.0f;   // in log2 units: P stays below 2^8
 
 struct AttnParams {
-  __nv_bfloat16* o;
+  // output row r goes to o_peers[r / rows_per_rank] at local row r % rows_per_rank, column col0 + head*128: a single
+  // destination for the one-GPU path; under context parallelism (cp.cu) the GPU that owns the token (P2P store)
+  void* o_peers[DRB_CP_MAX_RANKS];
   int64_t ld_o;
   int q_len, kv_len;
+  int rows_per_rank, col0;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -404,7 +407,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_after();
     const int row = q0 + t * kTileQ + quad * 32 + lane;
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* dst = p.o + static_cast<int64_t>(row) * p.ld_o + head * kHeadDim;
+    __nv_bfloat16* dst = nullptr;
+    if (row < p.q_len) {
+      const int owner = row / p.rows_per_rank;
+      dst = static_cast<__nv_bfloat16*>(p.o_peers[owner]) + static_cast<int64_t>(row - owner * p.rows_per_rank) * p.ld_o + p.col0 +
+            head * kHeadDim;
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -435,15 +443,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }  // namespace
 }  // namespace drb
 
-extern "C" int drb_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
-                                  int q_len, int kv_len, int num_heads, void* stream) {
+static int attention_launch(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
+                            int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0, void* stream) {
   using namespace drb;
-  DRB_REQUIRE(q && k && v && o, "null pointer");
+  DRB_REQUIRE(q && k && v && o_peers, "null pointer");
   DRB_REQUIRE(q_len > 0 && kv_len > 0 && num_heads > 0, "q_len, kv_len, num_heads must be positive");
-  DRB_REQUIRE(ld_qkv % 8 == 0 && ld_o % 8 == 0, "row pitches must be multiples of 8 elements");
-  DRB_REQUIRE(ld_qkv >= static_cast<int64_t>(num_heads) * kHeadDim && ld_o >= static_cast<int64_t>(num_heads) * kHeadDim,
+  DRB_REQUIRE(ld_qkv % 8 == 0 && ld_o % 8 == 0 && col0 % 8 == 0 && col0 >= 0, "row pitches / column offset must be multiples of 8 elements");
+  DRB_REQUIRE(ld_qkv >= static_cast<int64_t>(num_heads) * kHeadDim && ld_o >= col0 + static_cast<int64_t>(num_heads) * kHeadDim,
               "row pitch smaller than num_heads * 128");
-  DRB_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0, "o not 16-byte aligned");
+  DRB_REQUIRE(world >= 1 && world <= DRB_CP_MAX_RANKS && rows_per_rank > 0 &&
+                  static_cast<int64_t>(rows_per_rank) * world >= q_len, "rows_per_rank * world must cover q_len");
+  AttnParams p{};
+  for (int i = 0; i < world; ++i) {
+    DRB_REQUIRE(o_peers[i] != nullptr && (reinterpret_cast<uintptr_t>(o_peers[i]) & 15) == 0, "o not 16-byte aligned");
+    p.o_peers[i] = o_peers[i];
+  }
+  p.ld_o = ld_o;
+  p.q_len = q_len;
+  p.kv_len = kv_len;
+  p.rows_per_rank = rows_per_rank;
+  p.col0 = col0;
   CUtensorMap tq, tk, tv;
   const uint64_t cols = static_cast<uint64_t>(num_heads) * kHeadDim;
   int rc = make_tmap_2d_bf16(&tq, q, q_len, cols, ld_qkv, kTileQ, 64);
@@ -464,7 +483,6 @@ extern "C" int drb_attention_bf16(const void* q, const void* k, const void* v, i
     DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x4924u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x5555u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   }
-  AttnParams p{static_cast<__nv_bfloat16*>(o), ld_o, q_len, kv_len};
   dim3 grid((q_len + kTileQ * kQTilesPerCta - 1) / (kTileQ * kQTilesPerCta), num_heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (variant) {
@@ -475,6 +493,18 @@ extern "C" int drb_attention_bf16(const void* q, const void* k, const void* v, i
   }
   DRB_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int drb_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                                  int q_len, int kv_len, int num_heads, void* stream) {
+  void* peers[1] = {o};
+  return attention_launch(q, k, v, ld_qkv, peers, 1, ld_o, q_len, kv_len, num_heads, 0x7fffffff, 0, stream);
+}
+
+extern "C" int drb_attention_bf16_cp(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
+                                     int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0,
+                                     void* stream) {
+  return attention_launch(q, k, v, ld_qkv, o_peers, world, ld_o, q_len, kv_len, num_heads, rows_per_rank, col0, stream);
 }
 
 #ifdef DRB_ATTN_PROFILE

@@ -208,26 +208,41 @@ class CleanDiffusionRendererModel(nn.Module):
             raise ValueError("the B200 sampler needs a bfloat16 CUDA latent (no CPU fallback)")
         T, H, W = net._check_input(xt)
         net._ensure_packed()
-        ws = net._workspace(T, H, W, xt.device)
+        # context parallelism (net.enable_context_parallel): this rank owns latent frames [t0, t1); the Euler update is
+        # token-local, so the latent stays sharded through the whole loop and is gathered once at the end
+        cp = net._cp
+        t0, t1 = 0, T
+        if cp is not None:
+            from .context_parallel import shard_frames
+            t0, t1 = shard_frames(T, cp.rank, cp.world)
+        Tl = t1 - t0
+        ws = net._workspace(Tl, H, W, xt.device, cp)
         sig = sig.to(device=xt.device, dtype=torch.float32).contiguous()
-        x = xt[0].contiguous().clone()
+
+        def local(t5: Optional[Tensor]) -> Optional[Tensor]:
+            return None if t5 is None else t5[:, :, t0:t1]
+
+        def full(x_local: Tensor) -> Tensor:
+            return (x_local if cp is None else cp.all_gather_frames(x_local)).unsqueeze(0)
+
+        x = local(xt)[0].contiguous().clone()
         n = sig.numel() - 1
         passes = [cond] if uncond is None else [cond, uncond]
         ctx = [net.context_token(c.get("context_index")) for c in passes]
         y_c = torch.empty_like(ws["y"]) if uncond is not None else None
         if uncond is None:   # constants of the pass, hoisted out of the step loop
-            net.prepare_condition(ws, cond.get("latent_condition"), T, H, W)
+            net.prepare_condition(ws, local(cond.get("latent_condition")), Tl, H, W)
             use_ca = net.prepare_context(ws, ctx[0])
         for i in range(n):
             if teacher is not None:
-                x = teacher[i][0].contiguous().clone()
+                x = local(teacher[i])[0].contiguous().clone()
             s_i, s_n = sig[i:i + 1], sig[i + 1:i + 2]
             if uncond is None:
                 net.denoise_step(ws, x, s_i, s_n, use_ca)
             else:
                 net.modulation(ws, s_i)
                 for k, c in enumerate(passes):
-                    net.prepare_condition(ws, c.get("latent_condition"), T, H, W)
+                    net.prepare_condition(ws, local(c.get("latent_condition")), Tl, H, W)
                     use_ca = net.prepare_context(ws, ctx[k])
                     ops.scale_patchify(x, s_i, ws["tok"])
                     y = net.run_blocks(ws, use_ca)
@@ -235,5 +250,5 @@ class CleanDiffusionRendererModel(nn.Module):
                         y_c.copy_(y)
                 ops.unpatchify_euler(y_c, y, guidance, s_i, s_n, x, x)
             if per_step is not None:
-                per_step.append(x.unsqueeze(0).clone())
-        return x.unsqueeze(0)
+                per_step.append(full(x).clone())
+        return full(x)

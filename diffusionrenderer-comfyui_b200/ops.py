@@ -316,3 +316,26 @@ def cl_to_planar(x: torch.Tensor, C: int, scale: float = 1.0) -> torch.Tensor:
     out = torch.empty((C, T, H, W), device=x.device, dtype=BF16)
     _lib.call("drb_cl_to_planar", x.data_ptr(), out.data_ptr(), C, c_pad, T * H * W, float(scale), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ context parallelism
+def qk_norm_rope_scatter(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor,
+                         num_heads: int, dst_ptrs, dst_ld: int, row0: int) -> None:
+    """norm + RoPE of the local token rows of qkv [S_loc, 3D]; head h's q/k/v go to dst_ptrs[h // (H/P)] (peer [S, dst_ld])"""
+    _req(qkv, "qkv"), _req(wq, "wq"), _req(wk, "wk"), _req(cos_tab, "cos_tab"), _req(sin_tab, "sin_tab")
+    if cos_tab.shape[0] != qkv.shape[0] or not cos_tab.is_contiguous() or not sin_tab.is_contiguous():
+        raise ValueError("cos/sin tables must hold exactly the local token rows")
+    _lib.call("drb_cp_qk_norm_rope_scatter", qkv.data_ptr(), _rows2d(qkv, "qkv"), wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(),
+              sin_tab.data_ptr(), qkv.shape[0], num_heads, _lib.ptr_array(dst_ptrs), len(dst_ptrs), dst_ld, row0, _stream())
+
+
+def attention_cp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, o_ptrs, ld_o: int, rows_per_rank: int,
+                 col0: int) -> None:
+    """attention over the local heads and all tokens; output row r is stored to o_ptrs[r // rows_per_rank]"""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, n)
+    ld = _rows2d(q, "q")
+    if _rows2d(k, "k") != ld or _rows2d(v, "v") != ld:
+        raise ValueError("q, k, v must share one row pitch")
+    _lib.call("drb_attention_bf16_cp", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _lib.ptr_array(o_ptrs), len(o_ptrs), ld_o,
+              q.shape[0], k.shape[0], num_heads, rows_per_rank, col0, _stream())

@@ -56,6 +56,13 @@ int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
 int drb_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                        int q_len, int kv_len, int num_heads, void* stream);
 
+/* Context-parallel form (csrc/cp.cu): the same kernel over the H/P heads this GPU owns and all tokens;
+ * output row r is stored into o_peers[r / rows_per_rank] (a peer-mapped [rows_per_rank, ld_o] buffer of the GPU that
+ * owns token r) at local row r % rows_per_rank, column col0 + h*128 — the inverse Ulysses exchange is the epilogue. */
+#define DRB_CP_MAX_RANKS 8
+int drb_attention_bf16_cp(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
+                          int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0, void* stream);
+
 /* ---- fused elementwise family ----------------------------------------------------------------------------------
  * AdaLN: out = bf16(bf16(bf16(LN(x)) * bf16(1+scale)) + shift), LN over `D` without affine, eps 1e-6, fp32 stats
  * (CleanGeneralDIT.py:7-11,:481,:506).  If `add_vec` != NULL the residual stream is first updated in place,
@@ -180,6 +187,28 @@ int drb_temporal_attention_cl(const void* qkv, void* out, int T, int64_t hw, int
  * (the sigma_data factor of model_diffusion_renderer.py:146,156 rides along here). */
 int drb_planar_to_cl(const void* x, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
 int drb_cl_to_planar(const void* in, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
+
+/* ==== context parallelism over NVLink peer memory ==============================================
+ * One video's tokens are split contiguously over `world` GPUs (one process each).  Everything but self-attention is
+ * token-local; the Ulysses exchange around it is fused into the producing kernels as P2P stores. */
+
+/* drb_qk_norm_rope for the S_local tokens of this GPU, with head h's q / k / v rows stored into dst_ptrs[h / (H/world)]
+ * — the peer that owns the head — at row row0 + s of a [S, dst_ld] buffer laid out q | k | v, each (H/world)*128 wide.
+ * cos_tab / sin_tab: the rows of the local tokens.  Replaces CleanGeneralDIT.py:288-297 + the all-to-all. */
+int drb_cp_qk_norm_rope_scatter(const void* qkv, int64_t ld, const void* wq, const void* wk, const void* cos_tab,
+                                const void* sin_tab, int S_local, int num_heads, void* const* dst_ptrs, int world,
+                                int64_t dst_ld, int row0, void* stream);
+/* Device-side barrier between the `world` GPUs: flag_ptrs[j] is GPU j's flag array (uint32[world], peer-mapped, zeroed);
+ * every GPU passes the same, increasing `epoch`.  All earlier work of this stream (including P2P stores) is visible to
+ * the peers once they leave the barrier.  Never blocks the host. */
+int drb_cp_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, void* stream);
+/* Peer-shareable device memory: cudaMalloc (zero-filled) + CUDA IPC handle export / import (one process per GPU). */
+#define DRB_PEER_HANDLE_BYTES 64
+int drb_peer_alloc(int64_t bytes, void** ptr);
+int drb_peer_free(void* ptr);
+int drb_peer_export(const void* ptr, void* handle64);
+int drb_peer_import(const void* handle64, void** ptr);
+int drb_peer_close(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,103 @@
+"""Context-parallel check under torchrun (one rank per GPU): the CP forward and a 3-step sampler run must be bit-identical
+to the same model on one GPU; `--full` also times one 7B denoise step at 57x704x1280 under CP.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/cp_check.py --tiny"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--full", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from drb200 import diffusion_renderer_config as cfgm
+    from drb200.context_parallel import ContextParallel
+    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
+    cp = ContextParallel()
+    ok = True
+    if args.tiny:
+        cfg = cfgm.get_inverse_renderer_config(64, 96, 9)
+        cfg["model_type"] = "inverse"
+        cfg["net"].update(model_channels=1024, num_blocks=3, num_heads=8)
+        torch.manual_seed(0)
+        model = CleanDiffusionRendererModel(cfg).to(dev).to(torch.bfloat16)
+        model.net.init_weights_(seed=1)
+        T, H, W = 8, 12, 20
+        g = torch.Generator(device=dev).manual_seed(5)
+        x = torch.randn(1, 16, T, H, W, device=dev, generator=g).bfloat16()
+        cond = (torch.randn(1, 16, T, H, W, device=dev, generator=g) * 0.5).bfloat16()
+        ci = torch.full((1, 1), 2, dtype=torch.long, device=dev)
+        sigma = torch.tensor(1.26, device=dev)
+        with torch.no_grad():
+            ref = model.net(x=x, timesteps=sigma, latent_condition=cond, context_index=ci)
+            model.scheduler.set_timesteps(3, device=dev)
+            xt = x * model.scheduler.sigmas[0]
+            ref_z = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci}, None)
+            model.net.enable_context_parallel(cp)
+            got = model.net(x=x, timesteps=sigma, latent_condition=cond, context_index=ci)
+            got_z = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci}, None)
+            got_g = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci},
+                                        {"latent_condition": torch.zeros_like(cond), "context_index": torch.zeros_like(ci)}, guidance=2.0)
+            model.net.enable_context_parallel(None)
+            ref_g = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci},
+                                        {"latent_condition": torch.zeros_like(cond), "context_index": torch.zeros_like(ci)}, guidance=2.0)
+        torch.cuda.synchronize()
+        e = [bool(torch.equal(got, ref)), bool(torch.equal(got_z, ref_z)), bool(torch.equal(got_g, ref_g))]
+        print(f"rank {rank}/{world}: forward identical={e[0]} sampler identical={e[1]} cfg sampler identical={e[2]}", flush=True)
+        ok = all(e)
+    if args.full:
+        cfg = cfgm.get_inverse_renderer_config(704, 1280, 57)
+        cfg["model_type"] = "inverse"
+        with torch.device("meta"):
+            model = CleanDiffusionRendererModel(cfg)
+        model = model.to_empty(device=dev).to(torch.bfloat16)
+        net = model.net.init_weights_(seed=0)
+        net.enable_context_parallel(cp)
+        net._ensure_packed()
+        T, H, W = 8, 88, 160
+        Tl = T // world
+        ws = net._workspace(Tl, H, W, dev, cp)
+        g = torch.Generator(device=dev).manual_seed(1234)
+        cond = (torch.randn(1, 16, T, H, W, device=dev, generator=g) * 0.5).bfloat16()
+        model.scheduler.set_timesteps(15, device=dev)
+        sig = model.scheduler.sigmas.contiguous()
+        x = (torch.randn(16, T, H, W, device=dev, generator=g).bfloat16() * sig[0]).bfloat16()[:, rank * Tl:(rank + 1) * Tl].contiguous()
+        net.prepare_condition(ws, cond[:, :, rank * Tl:(rank + 1) * Tl], Tl, H, W)
+        use_ca = net.prepare_context(ws, net.context_token(torch.zeros(1, 1, dtype=torch.long, device=dev)))
+        for i in range(3):
+            net.denoise_step(ws, x, sig[i:i + 1], sig[i + 1:i + 2], use_ca)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 6
+        e0.record()
+        for i in range(n):
+            net.denoise_step(ws, x, sig[3 + i:4 + i], sig[4 + i:5 + i], use_ca)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"CP{world} 7B denoise step 57x704x1280: {ms.item():.1f} ms/step (max over ranks), finite={bool(torch.isfinite(x.float()).all())}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0 and flag.item() == 1:
+        print("CP_CHECK_OK", flush=True)
+    cp.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
