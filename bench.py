@@ -2,12 +2,15 @@
 """bench.py — DiT denoise steps/s of the 7B inverse renderer on a synthetic 57x704x1280 clip (BASELINE.json configs[1]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload inverse7b|tiny]
+                    [--parallel dp|cp] [--no-video] [--no-cpu-baseline]
 
 A "step" is ONE EDM Euler denoise step of one G-buffer pass: the sigma-only AdaLN vectors, c_in scaling + patchify,
 the 28-block GeneralDIT forward over S = 28 160 tokens and the unpatchify + Euler update (guidance 0, the node
 default).  N > 1 (torchrun, one rank per GPU): the five G-buffer passes / independent clips are data-parallel, every
 rank runs its own pass with replicated weights and no data-path collective, so scaling is "weak" and `value` is the
-whole-job steps/s = N*K / max-over-ranks time.
+whole-job steps/s = N*K / max-over-ranks time.  `--parallel cp` instead splits ONE video's token sequence over the N GPUs
+(context parallelism: Ulysses exchange fused into the kernels over NVLink peer memory, csrc/cp.cu): every rank works on
+the same step, `value` = K / max time, scaling "strong".
 
 Keys beyond the base contract:
   roofline     the dominant kernel (flash attention, 53 % of the forward's FLOPs): algorithmic FLOPs per launch
@@ -18,6 +21,9 @@ Keys beyond the base contract:
                the timed region.
   cpu_baseline the oracle (CPU restatement of the reference) timed on the host cores on a bounded sample.
   step_tflops  whole-step achieved TFLOP/s (6.8132e14 algorithmic FLOP per step) and its fraction of the peak.
+  video        seconds per inverse-rendered video measured through the pipeline API (CleanDiffusionRendererPipeline
+               .generate_video x 5 G-buffer passes: H2D of the fp32 clip, tokenizer encode once, 15 Euler steps and one
+               decode + uint8 post-process + D2H per pass); with dp over N GPUs each rank renders ceil(5/N) passes.
 `--impl reference` times the reference's own CPU implementation of the path (the oracle port, all host threads).
 """
 from __future__ import annotations
@@ -168,11 +174,70 @@ def config_block(args, wl):
     return {"workload": f"{args.workload}: GeneralDIT D={wl['D']} L={wl['L']} heads={wl['H']}, inverse renderer, "
                         f"{wl['clip'][0]}x{wl['clip'][1]}x{wl['clip'][2]} clip -> latent 16x{t}x{h}x{w}, S={t * (h // 2) * (w // 2)} tokens, "
                         "guidance 0, 15-step sigma schedule, random-init weights",
-            "parallelism": f"dp{args.gpus} over G-buffer passes (replicated weights, no collective)" if args.gpus > 1 else "single GPU",
+            "parallelism": ("single GPU" if args.gpus <= 1 else
+                            f"cp{args.gpus}: one video's tokens split over the GPUs, Ulysses exchange fused into kernels over NVLink peer memory"
+                            if args.parallel == "cp" else f"dp{args.gpus} over G-buffer passes (replicated weights, no collective)"),
             "l2": "working set per kernel (>= 230 MB activations + 32..134 MB weights) exceeds the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+# DRAM traffic of one attention launch at S = 28 160, 32 heads, from the ncu --set full capture of this kernel
+# (profiles/r01_attention_ncu_raw.txt: dram__bytes_read.sum 696 MB + dram__bytes_write.sum 213 MB; algorithmic 923 MB)
+ATTN_NCU_TRAFFIC_BYTES = {(28160, 32): 909.0e6}
+
+
+def random_tokenizer(torch, dev):
+    """the CV8x8x8 tokenizer (105.6 M parameters) with random-init weights on `dev`"""
+    from drb200.CleanVAE import AutoencoderKLCosmos, CleanVAE
+    m = AutoencoderKLCosmos()
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+    vae = CleanVAE(model=m)
+    vae.to(dev)
+    vae.reset_dtype(torch.bfloat16)
+    return vae
+
+
+def time_video(torch, dist, model, wl, rank, world, dev):
+    """One inverse-rendered video through the pipeline API, dp over G-buffer passes: returns (seconds max over ranks,
+    passes of this rank, h2d bytes, d2h bytes)."""
+    from drb200.diffusion_renderer_pipeline import CleanDiffusionRendererPipeline
+    f, hh, ww = wl["clip"]
+    vae = random_tokenizer(torch, dev)
+    pipe = CleanDiffusionRendererPipeline(checkpoint_dir="", checkpoint_name="", model_type="inverse", vae_instance=vae,
+                                          model_instance=model, guidance=0.0, num_steps=15, seed=42)
+    clip = (torch.rand(1, 3, f, hh, ww, generator=torch.Generator().manual_seed(1234)) * 2 - 1).pin_memory()   # host, fp32
+    mine = [p for p in range(5) if p % world == rank]
+
+    def render(passes, steps):
+        pipe.num_steps = steps
+        out = None
+        with pipe.shared_conditions():
+            for p in passes:
+                batch = {"rgb": clip, "video": clip, "context_index": torch.full((1, 1), p, dtype=torch.long)}
+                out = pipe.generate_video(batch, normalize_normal=(p == 3), seed=42)       # uint8 (1,T,H,W,3) on the host
+        return out
+
+    render(mine[:1] or [0], 1)                      # warm-up: allocations, tensor maps, tokenizer weight packing
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = render(mine, 15)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    h2d = clip.numel() * 4 if mine else 0
+    d2h = (out.size if out is not None else 0) * len(mine)
+    pipe.vae_instance = None
+    model.vae = None
+    return dt.item(), len(mine), h2d, d2h
+
+
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
@@ -187,6 +252,7 @@ def run_b200(args, wl):
     from drb200 import diffusion_renderer_config as cfgm
     from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
 
+    cp_mode = args.parallel == "cp" and world > 1
     f, hh, ww = wl["clip"]
     cfg = cfgm.get_inverse_renderer_config(hh, ww, f)
     cfg["model_type"] = "inverse"
@@ -197,23 +263,33 @@ def run_b200(args, wl):
     net = model.net.init_weights_(seed=0)
     c, t, h, w = latent_shape(wl["clip"])
     S = t * (h // 2) * (w // 2)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # dp: rank r renders its own G-buffer pass of its own clip; cp: every rank holds the same clip and pass
+    g = torch.Generator(device=dev).manual_seed(1234 + (0 if cp_mode else rank))
     cond = (torch.randn(1, 16, t, h, w, device=dev, generator=g) * 0.5).bfloat16()
-    ctx_idx = torch.full((1, 1), rank % 5, dtype=torch.long, device=dev)       # rank r renders G-buffer r
+    ctx_idx = torch.full((1, 1), 0 if cp_mode else rank % 5, dtype=torch.long, device=dev)
     model.scheduler.set_timesteps(15, device=dev)
     sig = model.scheduler.sigmas.contiguous()
     x0 = (torch.randn(1, 16, t, h, w, device=dev, generator=g).bfloat16() * sig[0]).bfloat16()
 
+    cp = None
+    t0f, t1f = 0, t
+    if cp_mode:
+        from drb200.context_parallel import ContextParallel, shard_frames
+        cp = ContextParallel()
+        net.enable_context_parallel(cp)
+        t0f, t1f = shard_frames(t, rank, world)
+    tl = t1f - t0f
     net._ensure_packed()
-    ws = net._workspace(t, h, w, dev)
-    net.prepare_condition(ws, cond, t, h, w)
+    ws = net._workspace(tl, h, w, dev, cp)
+    net.prepare_condition(ws, cond[:, :, t0f:t1f], tl, h, w)
     use_ca = net.prepare_context(ws, net.context_token(ctx_idx))
-    x = x0[0].contiguous().clone()
+    x_start = x0[0][:, t0f:t1f].contiguous()
+    x = x_start.clone()
 
     def step(i, timers=None):
         k = i % 15
         if k == 0:
-            x.copy_(x0[0])
+            x.copy_(x_start)
         net.denoise_step(ws, x, sig[k:k + 1], sig[k + 1:k + 2], use_ca, timers)
 
     def sync():
@@ -239,7 +315,8 @@ def run_b200(args, wl):
     if not torch.isfinite(x.float()).all():
         raise SystemExit("non-finite latent after the timed steps")
 
-    # ---- e2e: the public net.forward call with pinned host buffers (H2D + D2H inside the timed region)
+    # ---- e2e: the public net.forward call with pinned host buffers (H2D + D2H inside the timed region); under cp every
+    # rank passes the same full tensors and receives the full F (frame slices are exchanged by the final all-gather)
     hx = x0.cpu().pin_memory()
     hcond = cond.cpu().pin_memory()
     hidx = ctx_idx.cpu().pin_memory()
@@ -258,7 +335,6 @@ def run_b200(args, wl):
     n_e2e = max(2, min(args.steps, 5))
     e2e_step(0)
     sync()
-    t0 = time.perf_counter()
     e0.record()
     for i in range(n_e2e):
         e2e_step(i)
@@ -268,35 +344,51 @@ def run_b200(args, wl):
     h2d = hx.numel() * 2 + hcond.numel() * 2 + hidx.numel() * 8 + 4
     d2h = hout.numel() * 2
 
+    video = None
+    if not args.no_video and not cp_mode:
+        net.enable_context_parallel(None)
+        v_s, v_passes, v_h2d, v_d2h = time_video(torch, dist, model, wl, rank, world, dev)
+        video = {"s_per_video": v_s, "passes_per_rank": -(-5 // world), "passes_rank0": v_passes, "steps_per_pass": 15,
+                 "h2d_bytes_rank0": v_h2d, "d2h_bytes_rank0": v_d2h,
+                 "api": "CleanDiffusionRendererPipeline.generate_video per G-buffer pass (host fp32 clip in, host uint8 frames out), "
+                        "tokenizer encode once + 15 Euler steps + decode + post-process per pass; random-init tokenizer"}
+
     t_loc = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_loc, op=dist.ReduceOp.MAX)
     ms_max, e2e_max = t_loc.tolist()
     if rank == 0:
         pk = peaks()
-        steps_per_s = world * args.steps / (ms_max / 1e3)
+        units = 1 if cp_mode else world                       # videos-in-flight: cp works on one step together
+        steps_per_s = units * args.steps / (ms_max / 1e3)
         F = flops_per_forward(wl["D"], wl["L"], S)
-        attn_flops = 4.0 * S * S * wl["D"]
+        heads_local = wl["H"] // world if cp_mode else wl["H"]
+        attn_flops = 4.0 * S * S * 128 * heads_local
         peak = pk["bf16_tflops_sustained"]
         ach = attn_flops / (attn_ms / 1e3) / 1e12
+        step_tf = F * steps_per_s / 1e12 / world              # per-GPU achieved TFLOP/s
         line = {
             "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": config_block(args, wl),
-            "e2e": {"value": world * n_e2e / (e2e_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if cp_mode else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_block(args, wl),
+            "e2e": {"value": units * n_e2e / (e2e_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "CleanDiffusionRendererGeneralDIT.forward(x, timesteps, latent_condition, context_index) with pinned host tensors"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "attention_kernel (drb_attention_bf16)", "achieved": ach, "peak": peak,
-                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+                         "unit": "TFLOP/s", "frac": ach / peak,
+                         "traffic": ATTN_NCU_TRAFFIC_BYTES.get((S, heads_local)),
+                         "traffic_source": "profiles/r01_attention_ncu_raw.txt (ncu --set full, dram read + write per launch, bytes)",
+                         "peak_source": pk["source"] + " sustained bf16",
                          "launch_ms": attn_ms, "launches_timed": len(timers), "flops_per_launch": attn_flops,
                          "share_of_step": attn_ms * wl["L"] / (ms / args.steps)},
-            "step_tflops": {"achieved": F * (args.steps / (ms / 1e3)) / 1e12, "flops_per_step": F,
-                            "frac_of_sustained_peak": F * (args.steps / (ms / 1e3)) / 1e12 / peak,
-                            "frac_of_burst_peak": F * (args.steps / (ms / 1e3)) / 1e12 / pk["bf16_tflops"]},
-            # one inverse video = 5 G-buffer passes x 15 steps; with dp over passes a GPU runs ceil(5/N) of them
-            "s_per_video": -(-5 // world) * 15 / (steps_per_s / world),
+            "step_tflops": {"achieved_per_gpu": step_tf, "flops_per_step": F, "frac_of_sustained_peak": step_tf / peak,
+                            "frac_of_burst_peak": step_tf / pk["bf16_tflops"]},
+            # one inverse video = 5 G-buffer passes x 15 steps (DiT only; the measured end-to-end figure is `video`)
+            "s_per_video_dit_only": 5 * 15 / steps_per_s if cp_mode else -(-5 // world) * 15 / (steps_per_s / world),
             "clocks": clk.summary(),
         }
+        if video is not None:
+            line["video"] = video
         if world == 1 and not args.no_cpu_baseline:
             try:
                 v, info, _ = cpu_reference_sample(wl, 2, 1, 1 if args.workload == "tiny" else 4)
@@ -304,6 +396,8 @@ def run_b200(args, wl):
             except Exception as e:   # the GPU number stands on its own; say why the CPU leg is missing
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line))
+    if cp is not None:
+        cp.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -316,6 +410,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="inverse7b", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-video", action="store_true", help="skip the measured end-to-end video leg")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "cp"],
+                    help="N > 1: dp = one G-buffer pass per GPU (weak scaling, default); cp = one video split over the GPUs")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
