@@ -39,6 +39,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and "NCCL_DEBUG_FILE" not in os.environ:
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 
 WORKLOADS = {
     # name: (model_channels, blocks, heads, (frames, height, width))
