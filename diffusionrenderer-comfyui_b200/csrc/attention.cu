@@ -9,9 +9,9 @@
 //   warp 2        TMEM allocator (all 512 columns: S_0 | S_1 | O_0 | O_1, each 128 fp32 columns; P_t aliases S_t)
 //   warps 4..7    softmax warpgroup of tile 0 (one query row per thread)
 //   warps 8..11   softmax warpgroup of tile 1
-// While warpgroup t exponentiates S_t(j), the tensor pipe runs P V and Q K^T of the other tile.  The running max is
-// lazy: O_t (in TMEM) is only rescaled when a row maximum grows by more than 2^8, which the owning softmax thread
-// does itself between s_full and p_full, when O_t is quiescent.
+// While warpgroup t exponentiates S_t(j), the tensor pipe runs P V and Q K^T of the other tile.  The softmax reference is
+// lazy and max-free: tile 0 fixes it at the exact row maximum, later it moves (and O_t, in TMEM, is rescaled by the owning
+// softmax thread between s_full and p_full, when O_t is quiescent) only after a tile whose row sum reached 2^8.
 //
 // Roofline: tensor pipe, 4*q_len*kv_len*128 flop per head.
 #include <stdlib.h>
@@ -33,7 +33,6 @@ constexpr int kKvSlots = 5;
 constexpr int kAttnThreads = 384;
 constexpr int kAttnSmem = kQTilesPerCta * kTileBytes + kKvSlots * kTileBytes + 1024 + 256;
 constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // log2(e) / sqrt(128)
-constexpr float kRescaleThreshold = 8.0f;   // in log2 units: P stays below 2^8
 
 struct AttnParams {
   // output row r goes to o_peers[r / rows_per_rank] at local row r % rows_per_rank, column col0 + head*128: a single
@@ -296,7 +295,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_off + t * 128;
     const uint32_t o_tmem = tmem_base + lane_off + 256 + t * 128;
-    float m_ref = -INFINITY, l = 0.f;
+    // Reference M (log2 domain: P = 2^(s*c - M)) is LAZY and max-free: tile 0 sets it to the exact row maximum; afterwards
+    // it only moves when the previous tile's row sum reached 2^8 (checked at the top of the next iteration, when O_t is
+    // quiescent), by log2 of that sum — within 2^7 of the true maximum, and any reference both P and l share is exact
+    // algebra.  The fast path therefore has no max instruction at all (FMNMX is half rate and the FMA/ALU pipe, not
+    // MUFU alone, is what bounds the softmax: tools/ubench), and a tile's P may exceed 2^8 only by the growth inside
+    // that one tile, which the fp32 / bf16 exponent absorbs.
+    float M = 0.f, l = 0.f, prev_sum = 0.f;
     PROF_DECL;
     for (int j = 0; j < n_kv; ++j) {
       PROF(0);
@@ -306,10 +311,44 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld32(s_tmem, s0);
       tmem_ld32(s_tmem + 32, s1);
-      tmem_wait_ld();
-      tmem_ld32(s_tmem + 64, s2);       // in flight while the first half is exponentiated
-      tmem_ld32(s_tmem + 96, s3);
       const int valid = p.kv_len - j * kTileKV;    // >= 128 except on a ragged last tile
+      if (j == 0) {
+        tmem_ld32(s_tmem + 64, s2);
+        tmem_ld32(s_tmem + 96, s3);
+        tmem_wait_ld();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(s0[i]));
+          if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(s1[i]));
+          if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(s2[i]));
+          if (96 + i < valid) mx = fmaxf(mx, __uint_as_float(s3[i]));
+        }
+        M = mx * kScaleLog2;
+      } else {
+        const bool grow = !(prev_sum < 256.0f);
+        if (__any_sync(0xffffffffu, grow)) {
+          // rescale the running sum and this row of O_t (quiescent: P_t V_{j-1} completed before s_full fired)
+          const float g = grow ? __log2f(fminf(prev_sum, 3.0e38f)) : 0.f;
+          const float alpha = ex2(-g);
+          M += g;
+          l *= alpha;
+          tmem_wait_ld();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_tmem + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_tmem + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+        tmem_wait_ld();
+        tmem_ld32(s_tmem + 64, s2);       // in flight while the first half is exponentiated
+        tmem_ld32(s_tmem + 96, s3);
+      }
       if (valid < kTileKV) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -317,20 +356,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (32 + i >= valid) s1[i] = 0xff800000u;
         }
       }
-      // SPECULATIVE exponentials: P is computed against the running reference maximum m_ref of the previous tiles
-      // while this tile's row maximum is reduced alongside (independent instructions that fill the issue slots the
-      // MUFU-bound exponentials leave free).  Only if the maximum grew by more than 2^8 (rare after the first tiles;
-      // always on j == 0, where m_ref = -inf) is the work redone against the new reference, after rescaling O_t.
       const uint64_t scale2 = pack2(kScaleLog2, kScaleLog2);
-      uint64_t negm2 = pack2(-m_ref * kScaleLog2, -m_ref * kScaleLog2);
+      const uint64_t negm2 = pack2(-M, -M);
       uint64_t sum_a = pack2(0.f, 0.f), sum_b = pack2(0.f, 0.f);
       uint32_t pk[32], pk2[32];
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));
-        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
-      }
       softmax_chunk<kPolyMask>(s0, scale2, negm2, pk, sum_a);
       softmax_chunk<kPolyMask>(s1, scale2, negm2, pk + 16, sum_b);
       tmem_st32(s_tmem, pk);        // P_t columns [0,32): keys 0..63
@@ -343,44 +372,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (96 + i >= valid) s3[i] = 0xff800000u;
         }
       }
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s2[i + 1])));
-        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s3[i]), __uint_as_float(s3[i + 1])));
-      }
       softmax_chunk<kPolyMask>(s2, scale2, negm2, pk2, sum_a);
       PROF(3);
-      {
-        const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
-        const bool grow = (m_new - m_ref) * kScaleLog2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {
-          // slow path: new reference; rescale the running sum and this row of O_t (quiescent: P_t V_{j-1} completed
-          // before s_full fired), then redo the three speculative chunks
-          const float alpha = ex2((m_ref - m_new) * kScaleLog2);
-          l *= alpha;
-          m_ref = m_new;
-          if (j > 0) {
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[32];
-              tmem_ld32(o_tmem + c * 32, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(o_tmem + c * 32, o);
-            }
-          }
-          negm2 = pack2(-m_ref * kScaleLog2, -m_ref * kScaleLog2);
-          sum_a = pack2(0.f, 0.f);
-          sum_b = pack2(0.f, 0.f);
-          softmax_chunk<kPolyMask>(s0, scale2, negm2, pk, sum_a);
-          softmax_chunk<kPolyMask>(s1, scale2, negm2, pk + 16, sum_b);
-          tmem_wait_st();
-          tmem_st32(s_tmem, pk);
-          softmax_chunk<kPolyMask>(s2, scale2, negm2, pk2, sum_a);
-        }
-      }
-      PROF(4);
       tmem_wait_st();               // first half landed while chunk 2 was computed: hand it to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -393,7 +386,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         float a0, a1, b0, b1;
         unpack2(sum_a, a0, a1);
         unpack2(sum_b, b0, b1);
-        l += (a0 + a1) + (b0 + b1);
+        prev_sum = (a0 + a1) + (b0 + b1);
+        l += prev_sum;
       }
       tmem_wait_st();
       tc_fence_before();
@@ -440,6 +434,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
+
 }  // namespace
 }  // namespace drb
 
@@ -471,26 +466,30 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, kTileKV, 64);
   if (rc) return rc;
-  // fraction of the exponentials computed on the FMA pipe: 5/16 by default (tuned on B200); the
-  // DRB_ATTN_POLY environment variable selects another instantiation for tuning runs only.
+  // fraction of the exponentials computed on the FMA pipe; DRB_ATTN_POLY (0 -> 0/16, 1 -> 4/16, 2 -> 5/16, 3 -> 8/16,
+  // 4 -> 3/16, 5 -> 2/16) is a tuning switch only, the default is what was measured fastest on B200.
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("DRB_ATTN_POLY");
     variant = e ? atoi(e) : 2;
-    if (variant < 0 || variant > 3) variant = 2;
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x0000u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x1111u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x4924u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<0x5555u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    if (variant < 0 || variant > 5) variant = 2;
+#define DRB_ATTN_CFG(mask) \
+    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<mask>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    DRB_ATTN_CFG(0x0000u) DRB_ATTN_CFG(0x1111u) DRB_ATTN_CFG(0x4924u) DRB_ATTN_CFG(0x5555u) DRB_ATTN_CFG(0x0421u) DRB_ATTN_CFG(0x0101u)
+#undef DRB_ATTN_CFG
   }
   dim3 grid((q_len + kTileQ * kQTilesPerCta - 1) / (kTileQ * kQTilesPerCta), num_heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define DRB_ATTN_LAUNCH(mask) attention_kernel<mask><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p);
   switch (variant) {
-    case 0: attention_kernel<0x0000u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
-    case 1: attention_kernel<0x1111u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
-    case 3: attention_kernel<0x5555u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
-    default: attention_kernel<0x4924u><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p); break;
+    case 0: DRB_ATTN_LAUNCH(0x0000u) break;
+    case 1: DRB_ATTN_LAUNCH(0x1111u) break;
+    case 3: DRB_ATTN_LAUNCH(0x5555u) break;
+    case 4: DRB_ATTN_LAUNCH(0x0421u) break;
+    case 5: DRB_ATTN_LAUNCH(0x0101u) break;
+    default: DRB_ATTN_LAUNCH(0x4924u) break;
   }
+#undef DRB_ATTN_LAUNCH
   DRB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,6 +1,6 @@
 """Phase breakdown of the attention kernel (tuning aid).  Needs a library built with -DDRB_ATTN_PROFILE:
     tools/build_prof.sh && DRB200_LIB=$PWD/tools/_prof/libdrb200_prof.so python tools/attn_profile.py
-Prints, for CTA (0,0), the cycles the softmax warp 4 and the MMA-issuing thread spent in each phase."""
+Prints, for CTA (0,0), the cycles softmax warp 4 and the MMA-issuing warp spent in each phase (see PROF(i) in attention.cu)."""
 import ctypes
 import os
 import sys
@@ -27,11 +27,12 @@ assert lib.drb_debug_attn_profile(buf) == 0
 v = list(buf)
 n = S // 128
 print(f"kernel {e0.elapsed_time(e1):.3f} ms; per kv-iteration cycles of CTA(0,0) ({n} iterations)")
-names = ["loop/other", "wait s_full", "ldtm+max", "rescale check", "exp chunks 0,1 + sttm", "exp chunk 2 + wait_st + arrive half0",
-         "exp chunk 3 + sttm", "wait_st + fence + arrive half1"]
+names = ["loop/other", "wait s_full", "ldtm + rescale check + exp chunks 0,1 + sttm", "wait_ld + exp chunk 2", "-",
+         "wait_st + fence + arrive half0", "exp chunk 3 + sttm", "sum + wait_st + fence + arrive half1"]
 tot = sum(v[:8])
 for nm, c in zip(names, v[:8]):
-    print(f"  softmax  {nm:40s} {c / n:8.1f}  ({100 * c / tot:4.1f}%)")
+    if nm != "-":
+        print(f"  softmax  {nm:40s} {c / n:8.1f}  ({100 * c / tot:4.1f}%)")
 print(f"  softmax  total {tot / n:.1f} cycles/iteration")
 names = ["issue + loop", "wait kv_full", "issue PV/QK (sum over t)", "wait p half0", "wait p half1", "-", "-", "-"]
 tot = sum(v[8:16])

@@ -5,5 +5,5 @@ cd "$(dirname "$0")/.."
 mkdir -p tools/_prof
 SRC=diffusionrenderer-comfyui_b200/csrc
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -DDRB_ATTN_PROFILE ${DRB_NVCC_EXTRA} -shared \
-  -o tools/_prof/libdrb200_prof.so $SRC/runtime.cu $SRC/gemm.cu $SRC/attention.cu $SRC/elementwise.cu
+  -o tools/_prof/libdrb200_prof.so $SRC/*.cu
 echo tools/_prof/libdrb200_prof.so
