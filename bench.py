@@ -47,6 +47,10 @@ WORKLOADS = {
     # name: (model_channels, blocks, heads, (frames, height, width))
     "inverse7b": dict(D=4096, L=28, H=32, clip=(57, 704, 1280)),
     "tiny": dict(D=512, L=4, H=4, clip=(9, 256, 256)),           # BASELINE configs[0] (parity / CPU-runnable case)
+    # BASELINE configs[4]: CV8x8x8 tokenizer encode + decode of a 121-frame 704x1280 clip per GPU (not the headline metric;
+    # `python bench.py --workload tokenizer121` prints its own line: clips/s, TFLOP/s of the implicit-GEMM convolutions)
+    "tokenizer121": dict(clip=(121, 704, 1280), enc_flop=3.566e13, dec_flop=6.128e13),
+    "tokenizer57": dict(clip=(57, 704, 1280), enc_flop=1.764e13, dec_flop=3.014e13),
 }
 METRIC = "dit_denoise_steps_per_s"
 UNIT = "steps/s"
@@ -405,6 +409,63 @@ def run_b200(args, wl):
         dist.destroy_process_group()
 
 
+def run_tokenizer(args, wl):
+    """encode + decode of one clip per GPU (data-parallel over clips, no collective): whole-job clips/s"""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from drb200 import _lib
+    vae = random_tokenizer(torch, dev)
+    f, hh, ww = wl["clip"]
+    x = (torch.rand(1, 3, f, hh, ww, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)) * 2 - 1).bfloat16()
+
+    def step():
+        return vae.decode(vae.encode(x))
+
+    for _ in range(max(3, args.warmup)):
+        y = step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.LAUNCHES
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            y = step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = peaks()
+        per = ms.item() / args.steps
+        tf = (wl["enc_flop"] + wl["dec_flop"]) / per / 1e9
+        print(json.dumps({
+            "metric": "tokenizer_encode_decode_clips_per_s", "value": world * 1e3 / per, "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": per, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: CV8x8x8 tokenizer encode + decode of a {f}x{hh}x{ww} clip per GPU, random-init weights",
+                       "parallelism": f"dp{world} over clips (no collective)" if world > 1 else "single GPU",
+                       "l2": "activations of 0.4 .. 1.8 GB per layer exceed the 126 MB L2; no explicit flush"},
+            "gpu_launches": _lib.LAUNCHES - l0,
+            "roofline": {"bound": "tensor", "kernel": "conv3d_kernel (drb_conv3d_cl), whole encode + decode", "achieved": tf,
+                         "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"], "traffic": None,
+                         "flops_per_step": wl["enc_flop"] + wl["dec_flop"]},
+            "finite": bool(torch.isfinite(y.float()).all()), "clocks": clk.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -418,7 +479,11 @@ def main():
                     help="N > 1: dp = one G-buffer pass per GPU (weak scaling, default); cp = one video split over the GPUs")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.workload.startswith("tokenizer"):
+        if args.impl == "reference":
+            raise SystemExit("the CPU reference arm is defined for the DiT workloads only")
+        run_tokenizer(args, wl)
+    elif args.impl == "reference":
         run_reference(args, wl)
     else:
         if args.warmup < 3:

@@ -89,3 +89,72 @@ def test_scheduler_sigmas_match_oracle():
     assert s.timesteps.numel() == 15 and s.sigmas[-1] == 0
     with pytest.raises(RuntimeError):
         CleanEDMEulerScheduler().step(torch.zeros(1), torch.tensor(1.0), torch.zeros(1))
+
+
+# ------------------------------------------------------------------------------------------------ tokenizer host logic
+def test_tokenizer_state_dict_layout_matches_the_restated_upstream_class():
+    from drb200.CleanVAE import AutoencoderKLCosmos
+    from oracle.vae_oracle import FULL_VAE, SMALL_VAE, vae_param_shapes
+    with torch.device("meta"):
+        full = AutoencoderKLCosmos()
+    sd = full.state_dict()
+    want = dict(vae_param_shapes(FULL_VAE))
+    assert set(sd) == set(want) and len(sd) == 310
+    assert all(tuple(sd[k].shape) == want[k] for k in want)
+    assert sum(v.numel() for v in sd.values()) == 105_653_696          # ~105.6 M
+    small = AutoencoderKLCosmos(encoder_block_out_channels=SMALL_VAE.encoder_block_out_channels,
+                                decode_block_out_channels=SMALL_VAE.decode_block_out_channels)
+    assert set(small.state_dict()) == set(dict(vae_param_shapes(SMALL_VAE)))
+    # only the first down block / the middle up block resample (8x = 4x Haar * 2x); attention only in the mid blocks
+    assert [(b["spatial"], b["temporal"]) for b in full.enc_plan] == [(True, True), (False, False), (False, False)]
+    assert [(b["spatial"], b["temporal"]) for b in full.dec_plan] == [(False, False), (True, True), (False, False)]
+    assert not any("attentions" in k and "mid_block" not in k for k in sd)
+
+
+def test_tokenizer_wrapper_surface_and_errors(tmp_path):
+    from drb200.CleanVAE import AutoencoderKLCosmos, CleanVAE
+    model = AutoencoderKLCosmos(encoder_block_out_channels=(64, 64, 64, 64), decode_block_out_channels=(64, 64, 64, 64))
+    vae = CleanVAE(model=model)
+    assert (vae.latent_ch, vae.spatial_compression_factor, vae.temporal_compression_factor) == (16, 8, 8)
+    assert [vae.get_latent_num_frames(n) for n in (1, 9, 57, 121)] == [1, 2, 8, 16]
+    assert [vae.get_pixel_num_frames(n) for n in (1, 2, 8, 16)] == [1, 9, 57, 121]
+    with pytest.raises(ValueError):
+        vae.encode(torch.zeros(3, 9, 32, 32))
+    with pytest.raises(ValueError):
+        vae.decode(torch.zeros(16, 2, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):                      # no CPU fallback
+        vae.encode(torch.zeros(1, 3, 9, 32, 32))
+    with pytest.raises(ValueError):
+        CleanVAE()
+    with pytest.raises(FileNotFoundError):
+        CleanVAE(model_path=str(tmp_path))
+    with pytest.raises(ValueError):
+        AutoencoderKLCosmos(patch_size=2)
+    # diffusers checkpoint directory: config.json + diffusion_pytorch_model.safetensors, strict key match
+    import json
+    from safetensors.torch import save_file
+    cfg = {"encoder_block_out_channels": [64, 64, 64, 64], "decode_block_out_channels": [64, 64, 64, 64], "_class_name": "AutoencoderKLCosmos"}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    sd = {k: torch.randn_like(v) for k, v in model.state_dict().items()}
+    save_file(sd, str(tmp_path / "diffusion_pytorch_model.safetensors"))
+    loaded = CleanVAE(model_path=str(tmp_path))
+    got = loaded.model.state_dict()
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    loaded.reset_dtype(torch.bfloat16)
+    assert next(loaded.model.parameters()).dtype == torch.bfloat16
+
+
+def test_conv_argument_block_matches_the_header():
+    """ctypes mirror of drb_conv3d_args: same field order as include/drb200.h, and bad blocks are rejected without a GPU"""
+    from drb200 import _lib
+    header = open(os.path.join(ROOT, "include", "drb200.h")).read()
+    body = header[header.index("typedef struct drb_conv3d_args {"):header.index("} drb_conv3d_args;")]
+    names = re.findall(r"\b([A-Za-z_]+)(?=[,;])", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    assert names == [f[0] for f in _lib.Conv3dArgs._fields_]
+    a = _lib.Conv3dArgs()
+    with pytest.raises(ValueError):
+        _lib.call("drb_conv3d_cl", a, None)                                # null pointers
+    with pytest.raises(ValueError):
+        _lib.call("drb_haar_patch", 8, 8, 3, 10, 32, 32, None)              # frames not 1 + 4k
+    with pytest.raises(ValueError):
+        _lib.call("drb_softmax_rows", 16, 12, 4, 12, 1.0, None)             # pitch not a multiple of 8
