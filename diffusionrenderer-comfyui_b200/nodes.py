@@ -2,9 +2,9 @@
 class names, INPUT_TYPES / RETURN_TYPES / FUNCTION / CATEGORY and method signatures, driving the B200 pipeline.
 
 ComfyUI (`comfy`, `folder_paths`) is imported lazily inside the methods that need it, so the classes import (and are
-testable) without a ComfyUI host.  Out of scope here, as in SURVEY.md §2: environment-map projection
-(`preprocess_envmap.py`, needs nvdiffrast) — `Cosmos1ForwardRenderer` accepts pre-computed `env_ldr` / `env_log`
-tensors in a dict, or uses the reference's preprocess_envmap module when one is importable.
+testable) without a ComfyUI host.  Environment maps are projected / tone-mapped on the device by this package's
+`preprocess_envmap.py` (no nvdiffrast); `Cosmos1ForwardRenderer` also accepts pre-computed `env_ldr` / `env_log` tensors
+in a dict.
 """
 from __future__ import annotations
 
@@ -148,15 +148,11 @@ class Cosmos1ForwardRenderer:
 
     @staticmethod
     def _environment(env_map, H, W, T, device, env_format, env_brightness, env_flip, env_rot):
-        """{'env_ldr','env_log'}: (T,H,W,3) in [0,1].  A dict input is taken as already projected/tonemapped."""
+        """{'env_ldr','env_log'}: (T,H,W,3) in [0,1] (reference nodes.py:283-298).  A dict input is taken as already
+        projected / tone-mapped; otherwise the B200 preprocess_envmap module does it on the device (no nvdiffrast)."""
         if isinstance(env_map, dict) and "env_ldr" in env_map and "env_log" in env_map:
             return env_map
-        try:
-            from . import preprocess_envmap as pe        # the reference module, if the user dropped it in (needs nvdiffrast)
-        except Exception as e:
-            raise NotImplementedError(
-                "environment-map projection is outside the B200 hot path (SURVEY.md §2 row 7): pass env_map as a dict "
-                "{'env_ldr','env_log'} of (T,H,W,3) tensors, or install the reference preprocess_envmap module") from e
+        from . import preprocess_envmap as pe
         if env_format == "proj":
             return pe.render_projection_from_panorama(env_input=env_map, resolution=(H, W), num_frames=T, device=device,
                                                       env_brightness=env_brightness, env_flip=env_flip, env_rot=env_rot)
@@ -174,7 +170,8 @@ class Cosmos1ForwardRenderer:
         batch = {keymap[n]: t.permute(0, 4, 1, 2, 3) * 2.0 - 1.0 for n, t in g5.items()}
         batch["video"] = batch["depth"]
         dev = g5["depth"].device
-        env = self._environment(env_map, H, W, T, dev, env_format, env_brightness, env_flip_horizontal, env_rotation)
+        env = self._environment(env_map, H, W, T, getattr(pipeline, "device", torch.device("cuda")), env_format, env_brightness,
+                                env_flip_horizontal, env_rotation)
         batch["env_ldr"] = (env["env_ldr"].permute(3, 0, 1, 2).unsqueeze(0) * 2.0 - 1.0).expand(B, -1, -1, -1, -1)
         batch["env_log"] = (env["env_log"].permute(3, 0, 1, 2).unsqueeze(0) * 2.0 - 1.0).expand(B, -1, -1, -1, -1)
         # the reference passes `resolution=` to a parameter named `res` (nodes.py:300, defect D2): positional here

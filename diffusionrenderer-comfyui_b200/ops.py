@@ -339,3 +339,37 @@ def attention_cp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: i
         raise ValueError("q, k, v must share one row pitch")
     _lib.call("drb_attention_bf16_cp", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _lib.ptr_array(o_ptrs), len(o_ptrs), ld_o,
               q.shape[0], k.shape[0], num_heads, rows_per_rank, col0, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ environment maps (fp32)
+def envmap_latlong_to_cubemap(latlong: torch.Tensor, brightness: float, flip: bool, roll_px: int, res: int = 512) -> torch.Tensor:
+    """latlong [He, We, 3] fp32 -> preprocessed cube map [6, res, res, 3]"""
+    _req(latlong, "latlong", torch.float32)
+    if latlong.ndim != 3 or latlong.shape[2] != 3 or not latlong.is_contiguous():
+        raise ValueError("latlong must be a contiguous [H, W, 3] tensor")
+    cube = torch.empty((6, res, res, 3), device=latlong.device, dtype=torch.float32)
+    _lib.call("drb_envmap_latlong_to_cubemap", latlong.data_ptr(), latlong.shape[0], latlong.shape[1], float(brightness), int(bool(flip)),
+              int(roll_px), cube.data_ptr(), res, _stream())
+    return cube
+
+
+def envmap_project(cube: torch.Tensor, H: int, W: int):
+    """cube [6, R, R, 3] fp32 -> (env_ldr, env_log), each [H, W, 3] in [0, 1]"""
+    _req(cube, "cube", torch.float32)
+    if cube.ndim != 4 or cube.shape[0] != 6 or cube.shape[1] != cube.shape[2] or cube.shape[3] != 3 or not cube.is_contiguous():
+        raise ValueError("cube must be a contiguous [6, R, R, 3] tensor")
+    ldr = torch.empty((H, W, 3), device=cube.device, dtype=torch.float32)
+    lg = torch.empty_like(ldr)
+    _lib.call("drb_envmap_project", cube.data_ptr(), cube.shape[1], ldr.data_ptr(), lg.data_ptr(), H, W, _stream())
+    return ldr, lg
+
+
+def envmap_tonemap(img: torch.Tensor, H: int, W: int):
+    """img [Hs, Ws, 3] fp32 -> bilinear resize to (H, W) + tone mapping: (env_ldr, env_log)"""
+    _req(img, "img", torch.float32)
+    if img.ndim != 3 or img.shape[2] != 3 or not img.is_contiguous():
+        raise ValueError("img must be a contiguous [H, W, 3] tensor")
+    ldr = torch.empty((H, W, 3), device=img.device, dtype=torch.float32)
+    lg = torch.empty_like(ldr)
+    _lib.call("drb_envmap_tonemap", img.data_ptr(), img.shape[0], img.shape[1], ldr.data_ptr(), lg.data_ptr(), H, W, _stream())
+    return ldr, lg

@@ -188,6 +188,20 @@ int drb_temporal_attention_cl(const void* qkv, void* out, int T, int64_t hw, int
 int drb_planar_to_cl(const void* x, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
 int drb_cl_to_planar(const void* in, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
 
+/* ==== environment-map conditioning of the forward renderer ===================================
+ * The reference projects the panorama with nvdiffrast (preprocess_envmap.py); these entry points do it on the device
+ * without it.  fp32, channels-last RGB.
+ * drb_envmap_latlong_to_cubemap: apply_hdr_preprocessing (:263-286: x brightness, NaN -> 0, clamp [0, 65504], optional
+ *   horizontal flip, roll by roll_px) + latlong_to_cubemap_official (:161-206) -> cube [6][R][R][3].
+ * drb_envmap_project: render_projection_from_panorama (:408-467) — pixel (h, w) of the (H, W) lat-long grid looks the
+ *   cube map up in direction -latlong_vec (linear filter, cube boundary), flipped in both axes — + hdr_mapping_official
+ *   (:119-140) -> env_ldr, env_log [H][W][3] in [0, 1].
+ * drb_envmap_tonemap: tonemap_image_direct (:469-526) — bilinear resize (align_corners=False) + the same tone mapping. */
+int drb_envmap_latlong_to_cubemap(const float* latlong, int He, int We, float brightness, int flip, int roll_px, float* cube,
+                                  int R, void* stream);
+int drb_envmap_project(const float* cube, int R, float* env_ldr, float* env_log, int H, int W, void* stream);
+int drb_envmap_tonemap(const float* src, int Hs, int Ws, float* env_ldr, float* env_log, int H, int W, void* stream);
+
 /* ==== context parallelism over NVLink peer memory ==============================================
  * One video's tokens are split contiguously over `world` GPUs (one process each).  Everything but self-attention is
  * token-local; the Ulysses exchange around it is fused into the producing kernels as P2P stores. */

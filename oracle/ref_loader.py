@@ -41,3 +41,21 @@ def load():
         dit.PytorchDotProductAttention.forward = patched
         dit.PytorchDotProductAttention._drb_patched = True
     return dit, cfg, mdl, pipe
+
+
+def load_envmap():
+    """The reference preprocess_envmap module with its absent third-party imports (nvdiffrast, imageio, cv2) stubbed:
+    only its pure-torch functions are usable, which is all the oracle pins."""
+    if not available():
+        raise RuntimeError(f"reference not found at {REFERENCE_DIR}")
+    if _PKG not in sys.modules:
+        pkg = types.ModuleType(_PKG)
+        pkg.__path__ = [REFERENCE_DIR]
+        sys.modules[_PKG] = pkg
+    for name in ("nvdiffrast", "nvdiffrast.torch", "imageio", "imageio.v3", "cv2", "OpenEXR", "Imath"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    return importlib.import_module(f"{_PKG}.preprocess_envmap")
