@@ -9,7 +9,7 @@ weights, packs them into kernel-friendly layouts, and sequences kernel launches 
 Per forward (reference call sites in brackets):
   sigma embedding + AdaLN-LoRA GEMVs for all 3L+1 sub-blocks at once   [:321-372, :483-501, :558-572]
   patchify [x | condition | ones] -> tokens, patch GEMM                  [:409-417, :669-678]
-  L x { AdaLN -> fused QKV GEMM -> per-head RMSNorm + RoPE -> flash attention -> out GEMM with gated residual;
+  L x { AdaLN -> fused QKV GEMM with per-head RMSNorm + RoPE in its epilogue -> flash attention -> out GEMM with gated residual;
         cross-attention collapsed to one vector per block (one-token context => softmax == 1) added inside the
         next AdaLN; AdaLN -> GEMM+GELU -> GEMM with gated residual }      [:268-306, :442-462, :492-517]
   final AdaLN -> GEMM (D -> 64) -> unpatchify                            [:567-590, :709-716]
@@ -266,14 +266,14 @@ class CleanGeneralDIT(nn.Module):
         cos, sin = self.pos_embedder.tables(T * world, H // 2, W // 2, BF16)
         cos, sin = cos[rank * S:(rank + 1) * S].contiguous(), sin[rank * S:(rank + 1) * S].contiguous()
         ws = {
-            "S": S, "tok": torch.zeros(S, kpad, device=dev, dtype=BF16), "x": new(S, D), "xm": new(S, D), "qkv": new(S, 3 * D),
+            "S": S, "tok": torch.zeros(S, kpad, device=dev, dtype=BF16), "x": new(S, D), "xm": new(S, D),
             "h": new(S, self.hidden), "y": new(S, self.out_patch_dim), "cos": cos, "sin": sin,
             "e": new(D), "emb": new(D), "t1": new(D), "lora": new(3 * D), "mod_h": new(3 * L + 1, self.adaln_lora_dim),
             "mod": new(3 * L + 1, 3 * D), "ca_tmp": new(L, D), "ca_vec": new(L, D), "sigma": new(1, dtype=torch.float32),
             "cp": cp,
         }
         if cp is None:
-            ws["attn"] = new(S, D)
+            ws["attn"], ws["qkv"] = new(S, D), new(S, 3 * D)
         else:
             ws["attn"], ws["attn_ptrs"] = cp.alloc("attn", (S, D))
             ws["a2a"], ws["a2a_ptrs"] = cp.alloc("a2a", (S * world, 3 * D // world))
@@ -316,16 +316,16 @@ class CleanGeneralDIT(nn.Module):
         ops.gemm(ws["tok"], self._packed["wx"], out=ws["x"])
 
     def stage_pre_attention(self, ws, i: int) -> None:
-        """AdaLN -> fused QKV GEMM -> per-head RMSNorm + RoPE (under context parallelism: stored to the head owners)"""
-        P, D, Hh, cp = self._packed, self.model_channels, self.num_heads, ws["cp"]
+        """AdaLN -> fused QKV GEMM whose epilogue does the per-head RMSNorm + RoPE of q and k (under context parallelism
+        it also stores every head's rows straight into the GPU that owns the head: the all-to-all is the epilogue)"""
+        P, D, cp = self._packed, self.model_channels, ws["cp"]
         m_sa = ws["mod"][3 * i]
         ops.adaln_modulate(ws["x"], m_sa[:D], m_sa[D:2 * D], out=ws["xm"])
-        ops.gemm(ws["xm"], P["qkv"][i], out=ws["qkv"])
         if cp is None:
-            ops.qk_norm_rope(ws["qkv"], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], Hh)
+            ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], out=ws["qkv"])
         else:
-            ops.qk_norm_rope_scatter(ws["qkv"], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], Hh, ws["a2a_ptrs"],
-                                     3 * D // cp.world, cp.rank * ws["S"])
+            ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], peer_ptrs=ws["a2a_ptrs"],
+                                   peer_ld=3 * D // cp.world, row0=cp.rank * ws["S"])
 
     def stage_attention(self, ws, i: int, timers: Optional[list] = None) -> None:
         D, Hh, cp = self.model_channels, self.num_heads, ws["cp"]

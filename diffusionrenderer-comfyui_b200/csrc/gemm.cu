@@ -46,6 +46,16 @@ struct GemmParams {
   const __nv_bfloat16* resid;
   int64_t ldr;
   const __nv_bfloat16* gate;
+  // DRB_EPI_QKV_NORM_ROPE only: N = 3*sect (q | k | v), per-head RMSNorm weights, RoPE tables [M,128]; with world > 0 the
+  // rows go to the GPU that owns the head (context parallelism: the Ulysses exchange is this epilogue's store)
+  const __nv_bfloat16* wq;
+  const __nv_bfloat16* wk;
+  const __nv_bfloat16* cos_tab;
+  const __nv_bfloat16* sin_tab;
+  int sect;
+  int world, heads_per_rank, row0;
+  int64_t peer_ld;
+  void* peers[DRB_CP_MAX_RANKS];
 };
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& m, int& n) {
@@ -200,6 +210,85 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool row_ok = row < p.M;
       __nv_bfloat16* out_row = p.out + static_cast<int64_t>(row) * p.ldo;
       const __nv_bfloat16* res_row = kEpi == DRB_EPI_GATED_RESIDUAL ? p.resid + static_cast<int64_t>(row) * p.ldr : nullptr;
+      if constexpr (kEpi == DRB_EPI_QKV_NORM_ROPE) {
+        // The 256-column tile is two whole heads of one section (q, k or v).  One thread owns one token row, so the
+        // per-head RMSNorm and the rotate-half partner (d <-> d +- 64) are thread-local: bf16(acc) -> norm -> RoPE with
+        // the roundings of CleanGeneralDIT.py:23-33, :67-80 (same arithmetic as qk_norm_rope_kernel).
+        const int sect = col0 / p.sect;
+        const int head0 = (col0 - sect * p.sect) >> 7;
+        const __nv_bfloat16* wn = sect == 1 ? p.wk : p.wq;
+        const __nv_bfloat16* crow = p.cos_tab + static_cast<int64_t>(row_ok ? row : 0) * 128;
+        const __nv_bfloat16* srow = p.sin_tab + static_cast<int64_t>(row_ok ? row : 0) * 128;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          if (col0 + hh * 128 >= p.N) break;   // warp-uniform
+          uint32_t r[4][32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld32(taddr + hh * 128 + c * 32, r[c]);
+          tmem_wait_ld();
+          float inv = 1.0f;
+          if (sect < 2) {
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = bf16_round(__uint_as_float(r[c][i]));
+                r[c][i] = __float_as_uint(x);
+                ss += x * x;
+              }
+            inv = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wn + c * 32 + g * 8));
+                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  r[c][g * 8 + 2 * j] = __float_as_uint(bf16_round(__uint_as_float(r[c][g * 8 + 2 * j]) * inv * bf16_lo(ww[j])));
+                  r[c][g * 8 + 2 * j + 1] = __float_as_uint(bf16_round(__uint_as_float(r[c][g * 8 + 2 * j + 1]) * inv * bf16_hi(ww[j])));
+                }
+              }
+          }
+          if (!row_ok) continue;
+          const int head = head0 + hh;
+          __nv_bfloat16* dst;
+          if (p.world > 0) {
+            const int owner = head / p.heads_per_rank;
+            dst = static_cast<__nv_bfloat16*>(p.peers[owner]) + static_cast<int64_t>(p.row0 + row) * p.peer_ld +
+                  static_cast<int64_t>(sect) * p.heads_per_rank * 128 + (head - owner * p.heads_per_rank) * 128;
+          } else {
+            dst = out_row + col0 + hh * 128;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t o[4];
+              if (sect < 2) {
+                const uint4 cv = *reinterpret_cast<const uint4*>(crow + c * 32 + g * 8);
+                const uint4 sv = *reinterpret_cast<const uint4*>(srow + c * 32 + g * 8);
+                const uint32_t cc[4] = {cv.x, cv.y, cv.z, cv.w}, sn[4] = {sv.x, sv.y, sv.z, sv.w};
+                const float sign = c < 2 ? -1.0f : 1.0f;           // rotate_half = cat(-x[64:], x[:64])
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i0 = g * 8 + 2 * j;
+                  const float a0 = bf16_round(__uint_as_float(r[c][i0]) * bf16_lo(cc[j]));
+                  const float a1 = bf16_round(__uint_as_float(r[c][i0 + 1]) * bf16_hi(cc[j]));
+                  const float b0 = bf16_round(sign * __uint_as_float(r[c ^ 2][i0]) * bf16_lo(sn[j]));
+                  const float b1 = bf16_round(sign * __uint_as_float(r[c ^ 2][i0 + 1]) * bf16_hi(sn[j]));
+                  o[j] = pack_bf16x2(a0 + b0, a1 + b1);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  o[j] = pack_bf16x2(__uint_as_float(r[c][g * 8 + 2 * j]), __uint_as_float(r[c][g * 8 + 2 * j + 1]));
+              }
+              *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < kBlockN / 32; ++c) {
         const int col = col0 + c * 32;
@@ -239,6 +328,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           *reinterpret_cast<uint4*>(out_row + cg) = make_uint4(o[0], o[1], o[2], o[3]);
         }
+      }
       }
       // release the accumulator stage to the MMA issuer (the leader's barrier)
       tc_fence_before();
@@ -296,6 +386,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     case DRB_EPI_STORE: return launch_gemm<kCtaGroup, DRB_EPI_STORE>(ta, tb, p, s);
     case DRB_EPI_GELU: return launch_gemm<kCtaGroup, DRB_EPI_GELU>(ta, tb, p, s);
     case DRB_EPI_GATED_RESIDUAL: return launch_gemm<kCtaGroup, DRB_EPI_GATED_RESIDUAL>(ta, tb, p, s);
+    case DRB_EPI_QKV_NORM_ROPE: return launch_gemm<kCtaGroup, DRB_EPI_QKV_NORM_ROPE>(ta, tb, p, s);
     default: return fail("drb_gemm_bf16", "unknown epilogue");
   }
 }
@@ -326,8 +417,55 @@ extern "C" int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, kBlockN / cta_group, kBlockK);
   if (rc) return rc;
-  GemmParams p{M, N, K, static_cast<__nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(resid), ldr,
-               static_cast<const __nv_bfloat16*>(gate)};
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.resid = static_cast<const __nv_bfloat16*>(resid);
+  p.ldr = ldr;
+  p.gate = static_cast<const __nv_bfloat16*>(gate);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return cta_group == 1 ? dispatch_epi<1>(epilogue, ta, tb, p, s) : dispatch_epi<2>(epilogue, ta, tb, p, s);
+}
+
+extern "C" int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int D,
+                                      int K, const void* wq, const void* wk, const void* cos_tab, const void* sin_tab,
+                                      void* const* peer_ptrs, int world, int64_t peer_ld, int row0, void* stream) {
+  using namespace drb;
+  DRB_REQUIRE(A && W && wq && wk && cos_tab && sin_tab, "null pointer");
+  DRB_REQUIRE(M > 0 && D > 0 && K > 0 && D % 256 == 0 && K % 8 == 0, "D must be a multiple of 256 (two heads per tile), K of 8");
+  DRB_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "row pitches must be multiples of 8 elements and cover K");
+  DRB_REQUIRE(((reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk) | reinterpret_cast<uintptr_t>(cos_tab) |
+                reinterpret_cast<uintptr_t>(sin_tab)) & 15) == 0, "norm weights / RoPE tables must be 16-byte aligned");
+  GemmParams p{};
+  p.M = M; p.N = 3 * D; p.K = K;
+  p.wq = static_cast<const __nv_bfloat16*>(wq);
+  p.wk = static_cast<const __nv_bfloat16*>(wk);
+  p.cos_tab = static_cast<const __nv_bfloat16*>(cos_tab);
+  p.sin_tab = static_cast<const __nv_bfloat16*>(sin_tab);
+  p.sect = D;
+  if (world > 0) {
+    DRB_REQUIRE(peer_ptrs != nullptr && world <= DRB_CP_MAX_RANKS && (D / 128) % world == 0 && row0 >= 0, "bad context-parallel arguments");
+    DRB_REQUIRE(peer_ld % 8 == 0 && peer_ld >= 3LL * D / world, "peer row pitch too small");
+    for (int i = 0; i < world; ++i) {
+      DRB_REQUIRE(peer_ptrs[i] != nullptr && (reinterpret_cast<uintptr_t>(peer_ptrs[i]) & 15) == 0, "bad peer pointer");
+      p.peers[i] = peer_ptrs[i];
+    }
+    p.world = world;
+    p.heads_per_rank = D / 128 / world;
+    p.row0 = row0;
+    p.peer_ld = peer_ld;
+  } else {
+    DRB_REQUIRE(out != nullptr && ldo % 8 == 0 && ldo >= 3LL * D && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "bad output buffer");
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+  }
+  const int cta_group = (M > 128) ? 2 : 1;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, A, M, K, lda, kBlockM, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, W, 3 * D, K, ldw, kBlockN / cta_group, kBlockK);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return cta_group == 1 ? launch_gemm<1, DRB_EPI_QKV_NORM_ROPE>(ta, tb, p, s) : launch_gemm<2, DRB_EPI_QKV_NORM_ROPE>(ta, tb, p, s);
 }

@@ -373,3 +373,30 @@ def envmap_tonemap(img: torch.Tensor, H: int, W: int):
     lg = torch.empty_like(ldr)
     _lib.call("drb_envmap_tonemap", img.data_ptr(), img.shape[0], img.shape[1], ldr.data_ptr(), lg.data_ptr(), H, W, _stream())
     return ldr, lg
+
+
+def qkv_gemm_norm_rope(a: torch.Tensor, w: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos_tab: torch.Tensor,
+                       sin_tab: torch.Tensor, out: Optional[torch.Tensor] = None, peer_ptrs=None, peer_ld: int = 0,
+                       row0: int = 0) -> Optional[torch.Tensor]:
+    """[q | k | v] = a[M,K] @ w[3D,K]^T with per-head RMSNorm + RoPE of q, k in the GEMM epilogue.  Plain: rows go to
+    out [M, 3D].  Context-parallel (`peer_ptrs`): head h's rows go to peer_ptrs[h // (H/P)] at row row0 + s (no `out`)."""
+    for t, n in ((a, "a"), (w, "w"), (wq, "wq"), (wk, "wk"), (cos_tab, "cos_tab"), (sin_tab, "sin_tab")):
+        _req(t, n)
+    M, K = a.shape
+    if w.shape[1] != K or w.shape[0] % 3:
+        raise ValueError(f"shape mismatch: a {tuple(a.shape)} vs w {tuple(w.shape)}")
+    D = w.shape[0] // 3
+    if cos_tab.shape != (M, 128) or sin_tab.shape != (M, 128) or not cos_tab.is_contiguous() or not sin_tab.is_contiguous():
+        raise ValueError("cos/sin tables must be contiguous [M, 128]")
+    if peer_ptrs is None:
+        if out is None:
+            out = torch.empty((M, 3 * D), device=a.device, dtype=BF16)
+        _req(out, "out")
+        _lib.call("drb_gemm_qkv_norm_rope", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), out.data_ptr(),
+                  _rows2d(out, "out"), M, D, K, wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), None, 0, 0, 0,
+                  _stream())
+        return out
+    _lib.call("drb_gemm_qkv_norm_rope", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), None, 0, M, D, K,
+              wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), _lib.ptr_array(peer_ptrs), len(peer_ptrs),
+              peer_ld, row0, _stream())
+    return None

@@ -31,6 +31,9 @@ extern "C" {
 #define DRB_EPI_STORE 0          /* out = bf16(acc)                                        nn.Linear, bias=False            */
 #define DRB_EPI_GELU 1           /* out = bf16(gelu_erf(bf16(acc)))                        CleanGeneralDIT.py:454-457       */
 #define DRB_EPI_GATED_RESIDUAL 2 /* out = bf16(resid + bf16(gate[n] * bf16(acc)))          CleanGeneralDIT.py:517           */
+#define DRB_EPI_QKV_NORM_ROPE 3  /* internal to drb_gemm_qkv_norm_rope                                                      */
+
+#define DRB_CP_MAX_RANKS 8 /* GPUs of one context-parallel group */
 
 const char* drb_last_error(void);
 int drb_version(void);
@@ -47,6 +50,16 @@ int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int M, int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
                   int cta_group, void* stream);
 
+/* Fused QKV projection: [q | k | v] = A[M,K] @ W[3D,K]^T with, in the epilogue, per-head RMSNorm of q and k (weights
+ * wq, wk [128], eps 1e-6) and RoPE from the bf16 tables cos_tab / sin_tab [M,128] — i.e. drb_gemm_bf16 followed by
+ * drb_qk_norm_rope without the round trip of q and k through HBM (CleanGeneralDIT.py:268-297).  world == 0: rows are
+ * stored to out [M, ldo >= 3D].  world > 0 (context parallelism): head h's q / k / v row of local token s is stored
+ * into peer_ptrs[h / (H/world)] at row row0 + s of a [S, peer_ld] buffer laid out q | k | v (each (H/world)*128 wide) —
+ * the Ulysses all-to-all is the GEMM's epilogue (P2P stores over NVLink, overlapping the MMA of the next tile). */
+int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int D,
+                           int K, const void* wq, const void* wk, const void* cos_tab, const void* sin_tab,
+                           void* const* peer_ptrs, int world, int64_t peer_ld, int row0, void* stream);
+
 /* ---- self-attention ------------------------------------------------------------------------------------------
  * o[s, h*128 + d] = softmax_j(q[s,h,:]·k[j,h,:] / sqrt(128)) v[j,h,d]; no mask, no dropout, head_dim 128.
  * Replaces PytorchDotProductAttention.forward / F.scaled_dot_product_attention (CleanGeneralDIT.py:181-203), with
@@ -59,7 +72,6 @@ int drb_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_q
 /* Context-parallel form (csrc/cp.cu): the same kernel over the H/P heads this GPU owns and all tokens;
  * output row r is stored into o_peers[r / rows_per_rank] (a peer-mapped [rows_per_rank, ld_o] buffer of the GPU that
  * owns token r) at local row r % rows_per_rank, column col0 + h*128 — the inverse Ulysses exchange is the epilogue. */
-#define DRB_CP_MAX_RANKS 8
 int drb_attention_bf16_cp(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
                           int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0, void* stream);
 

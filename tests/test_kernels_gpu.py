@@ -226,3 +226,33 @@ def test_postprocess_u8(normalize):
     diff = abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= (2 if normalize else 0)      # plain path is bit-exact; the normal blend may move 1 bf16 ulp
     assert (diff == 0).mean() >= 0.97
+
+
+@pytest.mark.parametrize("M,D,K", [(300, 256, 256), (1000, 512, 512), (77, 256, 136)])
+def test_fused_qkv_gemm_norm_rope_matches_the_unfused_kernels(M, D, K):
+    """drb_gemm_qkv_norm_rope == drb_gemm_bf16 followed by drb_qk_norm_rope, up to the summation order of the RMS"""
+    from drb200 import ops
+    g = gen(11)
+    H = D // 128
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(3 * D, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    wq = (1 + 0.1 * torch.randn(128, device=DEV, generator=g)).bfloat16()
+    wk = (1 + 0.1 * torch.randn(128, device=DEV, generator=g)).bfloat16()
+    ang = (torch.rand(M, 128, device=DEV, generator=g) * 6.28).bfloat16()
+    cos, sin = ang.cos().bfloat16().contiguous(), ang.sin().bfloat16().contiguous()
+    ref = ops.gemm(a, w)
+    ops.qk_norm_rope(ref, wq, wk, cos, sin, H)
+    got = ops.qkv_gemm_norm_rope(a, w, wq, wk, cos, sin)
+    assert torch.equal(got[:, 2 * D:], ref[:, 2 * D:])                      # v: plain projection
+    # the RMS is summed in a different order (one thread vs a warp tree): a flipped bf16 rounding of the normalised value
+    # can surface as 2 ulp after the two RoPE products on a handful of elements
+    assert_close_bf16(got[:, :2 * D], ref[:, :2 * D], max_ulp=2, min_exact=0.995)
+    # context-parallel form: rows scattered to the (virtual) head owners
+    world, S_tot, row0 = 2, M + 50, 13
+    Dp = D // world
+    bufs = [torch.zeros(S_tot, 3 * Dp, device=DEV, dtype=torch.bfloat16) for _ in range(world)]
+    ops.qkv_gemm_norm_rope(a, w, wq, wk, cos, sin, peer_ptrs=[b.data_ptr() for b in bufs], peer_ld=3 * Dp, row0=row0)
+    for r, b in enumerate(bufs):
+        for sect in range(3):
+            assert torch.equal(b[row0:row0 + M, sect * Dp:(sect + 1) * Dp], got[:, sect * D + r * Dp: sect * D + (r + 1) * Dp])
+        assert not b[:row0].any() and not b[row0 + M:].any()
