@@ -39,9 +39,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and "NCCL_DEBUG_FILE" not in os.environ:
-    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+# stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for everything else (NCCL prints its
+# "NCCL version ..." banner to fd 1 from C), and the result line is written to a private duplicate of the real stdout.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 WORKLOADS = {
     # name: (model_channels, blocks, heads, (frames, height, width))
@@ -173,7 +180,7 @@ def run_reference(args, wl):
             "dtype": "bf16", "data": "synthetic", "config": config_block(args, wl),
             "cpu_baseline": dict(info, value=value, unit=UNIT),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_block(args, wl):
@@ -402,7 +409,7 @@ def run_b200(args, wl):
                 line["cpu_baseline"] = dict(info, value=v, unit=UNIT)
             except Exception as e:   # the GPU number stands on its own; say why the CPU leg is missing
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        emit(line)
     if cp is not None:
         cp.close()
     if world > 1:
@@ -450,7 +457,7 @@ def run_tokenizer(args, wl):
         pk = peaks()
         per = ms.item() / args.steps
         tf = (wl["enc_flop"] + wl["dec_flop"]) / per / 1e9
-        print(json.dumps({
+        emit({
             "metric": "tokenizer_encode_decode_clips_per_s", "value": world * 1e3 / per, "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": per, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -461,7 +468,7 @@ def run_tokenizer(args, wl):
             "roofline": {"bound": "tensor", "kernel": "conv3d_kernel (drb_conv3d_cl), whole encode + decode", "achieved": tf,
                          "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"], "traffic": None,
                          "flops_per_step": wl["enc_flop"] + wl["dec_flop"]},
-            "finite": bool(torch.isfinite(y.float()).all()), "clocks": clk.summary()}))
+            "finite": bool(torch.isfinite(y.float()).all()), "clocks": clk.summary()})
     if world > 1:
         dist.destroy_process_group()
 

@@ -160,6 +160,7 @@ class CleanGeneralDIT(nn.Module):
         self._packed_key = None
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self._cp = None     # context_parallel.ContextParallel when one video is split over several GPUs
+        self.fuse_qkv_epilogue = True   # False: QKV GEMM, then the stand-alone norm + RoPE (+ scatter) kernel (A/B measurements)
 
     @torch.no_grad()
     def init_weights_(self, seed: int = 0) -> "CleanGeneralDIT":
@@ -321,7 +322,17 @@ class CleanGeneralDIT(nn.Module):
         P, D, cp = self._packed, self.model_channels, ws["cp"]
         m_sa = ws["mod"][3 * i]
         ops.adaln_modulate(ws["x"], m_sa[:D], m_sa[D:2 * D], out=ws["xm"])
-        if cp is None:
+        if not self.fuse_qkv_epilogue:
+            qkv = ws.get("qkv")
+            if qkv is None:
+                qkv = ws["qkv"] = torch.empty(ws["S"], 3 * D, device=ws["x"].device, dtype=BF16)
+            ops.gemm(ws["xm"], P["qkv"][i], out=qkv)
+            if cp is None:
+                ops.qk_norm_rope(qkv, P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], self.num_heads)
+            else:
+                ops.qk_norm_rope_scatter(qkv, P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], self.num_heads, ws["a2a_ptrs"],
+                                         3 * D // cp.world, cp.rank * ws["S"])
+        elif cp is None:
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], out=ws["qkv"])
         else:
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], peer_ptrs=ws["a2a_ptrs"],

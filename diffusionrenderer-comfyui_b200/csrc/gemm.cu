@@ -37,6 +37,9 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;                   // 48 KB / 32 KB
   static constexpr int kStages = kCtaGroup == 1 ? 4 : 6;                  // 192 KB of operand ring
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // the QKV epilogue stages one head per warp (32 rows x 256 B, 16-byte chunks XOR-swizzled by row) so that whole rows
+  // go out coalesced; only that instantiation allocates it
+  static constexpr int kEpiStageBytes = 4 * 32 * 256;
 };
 
 struct GemmParams {
@@ -83,6 +86,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_stage = smem + Cfg::kStages * Cfg::kStageBytes + 256;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -251,16 +255,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
               }
           }
-          if (!row_ok) continue;
-          const int head = head0 + hh;
-          __nv_bfloat16* dst;
-          if (p.world > 0) {
-            const int owner = head / p.heads_per_rank;
-            dst = static_cast<__nv_bfloat16*>(p.peers[owner]) + static_cast<int64_t>(p.row0 + row) * p.peer_ld +
-                  static_cast<int64_t>(sect) * p.heads_per_rank * 128 + (head - owner * p.heads_per_rank) * 128;
-          } else {
-            dst = out_row + col0 + hh * 128;
-          }
+          // RoPE (q, k) or plain rounding (v) into this warp's staging rows, then whole 256-byte head rows go out
+          // coalesced (two rows per store instruction) — to the local buffer, or over NVLink to the head's owner
+          uint8_t* my_stage = epi_stage + q * (32 * 256);
+          uint8_t* my_row = my_stage + lane * 256;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -285,8 +283,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int j = 0; j < 4; ++j)
                   o[j] = pack_bf16x2(__uint_as_float(r[c][g * 8 + 2 * j]), __uint_as_float(r[c][g * 8 + 2 * j + 1]));
               }
-              *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(my_row + (((c * 4 + g) ^ (lane & 15)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
+          __syncwarp();
+          const int head = head0 + hh;
+          const int row_base = row - lane;                          // first row of this warp's 32
+          int64_t dst_pitch;
+          __nv_bfloat16* dst0;
+          if (p.world > 0) {
+            const int owner = head / p.heads_per_rank;
+            dst_pitch = p.peer_ld;
+            dst0 = static_cast<__nv_bfloat16*>(p.peers[owner]) + static_cast<int64_t>(p.row0 + row_base) * p.peer_ld +
+                   static_cast<int64_t>(sect) * p.heads_per_rank * 128 + (head - owner * p.heads_per_rank) * 128;
+          } else {
+            dst_pitch = p.ldo;
+            dst0 = p.out + static_cast<int64_t>(row_base) * p.ldo + col0 + hh * 128;
+          }
+#pragma unroll 4
+          for (int it = 0; it < 16; ++it) {
+            const int rr = it * 2 + (lane >> 4);
+            if (row_base + rr < p.M)
+              *reinterpret_cast<uint4*>(dst0 + rr * dst_pitch + (lane & 15) * 8) =
+                  *reinterpret_cast<const uint4*>(my_stage + rr * 256 + (((lane & 15) ^ (rr & 15)) * 16));
+          }
+          __syncwarp();
         }
       } else {
 #pragma unroll 1
@@ -354,9 +374,11 @@ template <int kCtaGroup, int kEpi>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kCtaGroup>;
   auto kernel = gemm_bf16_kernel<kCtaGroup, kEpi>;
+  constexpr int kSmem = Cfg::kSmemBytes + (kEpi == DRB_EPI_QKV_NORM_ROPE ? Cfg::kEpiStageBytes : 0);
+  static_assert(kSmem <= 232448, "over the 227 KB shared-memory limit of sm_100");
   static bool configured = false;   // per template instance
   if (!configured) {
-    DRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    DRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const int tile_m_rows = kBlockM * kCtaGroup;
@@ -367,7 +389,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * kCtaGroup);
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

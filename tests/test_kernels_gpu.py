@@ -245,8 +245,11 @@ def test_fused_qkv_gemm_norm_rope_matches_the_unfused_kernels(M, D, K):
     got = ops.qkv_gemm_norm_rope(a, w, wq, wk, cos, sin)
     assert torch.equal(got[:, 2 * D:], ref[:, 2 * D:])                      # v: plain projection
     # the RMS is summed in a different order (one thread vs a warp tree): a flipped bf16 rounding of the normalised value
-    # can surface as 2 ulp after the two RoPE products on a handful of elements
-    assert_close_bf16(got[:, :2 * D], ref[:, :2 * D], max_ulp=2, min_exact=0.995)
+    # shows up as 1 ulp of a RoPE product, i.e. possibly several ulp of a sum that cancels — gate on the absolute scale
+    qk_got, qk_ref = got[:, :2 * D].float(), ref[:, :2 * D].float()
+    assert (qk_got == qk_ref).float().mean() >= 0.995
+    assert (qk_got - qk_ref).abs().max() <= 2.0 ** -7 * qk_ref.abs().max()
+    assert rel_l2(qk_got, qk_ref) <= 1e-3
     # context-parallel form: rows scattered to the (virtual) head owners
     world, S_tot, row0 = 2, M + 50, 13
     Dp = D // world
