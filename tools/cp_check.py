@@ -74,22 +74,26 @@ def main():
         x = (torch.randn(16, T, H, W, device=dev, generator=g).bfloat16() * sig[0]).bfloat16()[:, rank * Tl:(rank + 1) * Tl].contiguous()
         net.prepare_condition(ws, cond[:, :, rank * Tl:(rank + 1) * Tl], Tl, H, W)
         use_ca = net.prepare_context(ws, net.context_token(torch.zeros(1, 1, dtype=torch.long, device=dev)))
-        for i in range(3):
-            net.denoise_step(ws, x, sig[i:i + 1], sig[i + 1:i + 2], use_ca)
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 6
-        e0.record()
-        for i in range(n):
-            net.denoise_step(ws, x, sig[3 + i:4 + i], sig[4 + i:5 + i], use_ca)
-        e1.record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            print(f"CP{world} 7B denoise step 57x704x1280: {ms.item():.1f} ms/step (max over ranks), finite={bool(torch.isfinite(x.float()).all())}", flush=True)
+        for fused in (True, False, True, False):
+            net.fuse_qkv_epilogue = fused
+            for i in range(3):
+                net.denoise_step(ws, x, sig[i:i + 1], sig[i + 1:i + 2], use_ca)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 6
+            e0.record()
+            for i in range(n):
+                net.denoise_step(ws, x, sig[3 + i:4 + i], sig[4 + i:5 + i], use_ca)
+            e1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"CP{world} 7B denoise step 57x704x1280, QKV all-to-all {'in the GEMM epilogue' if fused else 'as a scatter kernel'}: "
+                      f"{ms.item():.1f} ms/step (max over ranks), finite={bool(torch.isfinite(x.float()).all())}", flush=True)
+        net.fuse_qkv_epilogue = True
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and flag.item() == 1:
