@@ -196,8 +196,8 @@ def config_block(args, wl):
 
 # ------------------------------------------------------------------------------------------------ B200 arm
 # DRAM traffic of one attention launch at S = 28 160, 32 heads, from the ncu --set full capture of this kernel
-# (profiles/r01_attention_ncu_raw.txt: dram__bytes_read.sum 696 MB + dram__bytes_write.sum 213 MB; algorithmic 923 MB)
-ATTN_NCU_TRAFFIC_BYTES = {(28160, 32): 909.0e6}
+# (profiles/r01_attention_final_ncu_raw.txt: dram__bytes_read.sum 704.1 MB + dram__bytes_write.sum 239.6 MB; algorithmic 923 MB)
+ATTN_NCU_TRAFFIC_BYTES = {(28160, 32): 943.6e6}
 
 
 def random_tokenizer(torch, dev):
@@ -391,7 +391,7 @@ def run_b200(args, wl):
             "roofline": {"bound": "tensor", "kernel": "attention_kernel (drb_attention_bf16)", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": ATTN_NCU_TRAFFIC_BYTES.get((S, heads_local)),
-                         "traffic_source": "profiles/r01_attention_ncu_raw.txt (ncu --set full, dram read + write per launch, bytes)",
+                         "traffic_source": "profiles/r01_attention_final_ncu_raw.txt (ncu --set full, dram read + write per launch, bytes)",
                          "peak_source": pk["source"] + " sustained bf16",
                          "launch_ms": attn_ms, "launches_timed": len(timers), "flops_per_launch": attn_flops,
                          "share_of_step": attn_ms * wl["L"] / (ms / args.steps)},
