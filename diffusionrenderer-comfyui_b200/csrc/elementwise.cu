@@ -25,7 +25,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 constexpr int kAdaMaxChunks = 16;
 constexpr int kAdaWarps = 8;
 
-__global__ void __launch_bounds__(kAdaWarps * 32)
+__global__ void __launch_bounds__(kAdaWarps * 32, 3)
 adaln_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ shift,
              const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ add_gate,
              const __nv_bfloat16* __restrict__ add_vec, int rows, int D) {
