@@ -190,7 +190,9 @@ def config_block(args, wl):
                         "guidance 0, 15-step sigma schedule, random-init weights",
             "parallelism": ("single GPU" if args.gpus <= 1 else
                             f"cp{args.gpus}: one video's tokens split over the GPUs, Ulysses exchange fused into kernels over NVLink peer memory"
-                            if args.parallel == "cp" else f"dp{args.gpus} over G-buffer passes (replicated weights, no collective)"),
+                            if args.parallel == "cp" else
+                            f"ring{args.gpus}: one video's tokens split over the GPUs, K/V blocks pulled from peer memory in ring order"
+                            if args.parallel == "ring" else f"dp{args.gpus} over G-buffer passes (replicated weights, no collective)"),
             "l2": "working set per kernel (>= 230 MB activations + 32..134 MB weights) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -266,7 +268,7 @@ def run_b200(args, wl):
     from drb200 import diffusion_renderer_config as cfgm
     from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
 
-    cp_mode = args.parallel == "cp" and world > 1
+    cp_mode = args.parallel in ("cp", "ring") and world > 1
     f, hh, ww = wl["clip"]
     cfg = cfgm.get_inverse_renderer_config(hh, ww, f)
     cfg["model_type"] = "inverse"
@@ -289,7 +291,7 @@ def run_b200(args, wl):
     t0f, t1f = 0, t
     if cp_mode:
         from drb200.context_parallel import ContextParallel, shard_frames
-        cp = ContextParallel()
+        cp = ContextParallel(mode="ring" if args.parallel == "ring" else "ulysses")
         net.enable_context_parallel(cp)
         t0f, t1f = shard_frames(t, rank, world)
     tl = t1f - t0f
@@ -377,6 +379,8 @@ def run_b200(args, wl):
         steps_per_s = units * args.steps / (ms_max / 1e3)
         F = flops_per_forward(wl["D"], wl["L"], S)
         heads_local = wl["H"] // world if cp_mode else wl["H"]
+        # per layer and rank: ulysses = all S x S for H/P heads (one launch); ring = S/P rows x S keys for all heads (P launches,
+        # timed together) — the same FLOPs
         attn_flops = 4.0 * S * S * 128 * heads_local
         peak = pk["bf16_tflops_sustained"]
         ach = attn_flops / (attn_ms / 1e3) / 1e12
@@ -482,8 +486,9 @@ def main():
     ap.add_argument("--workload", default="inverse7b", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true", help="skip the measured end-to-end video leg")
-    ap.add_argument("--parallel", default="dp", choices=["dp", "cp"],
-                    help="N > 1: dp = one G-buffer pass per GPU (weak scaling, default); cp = one video split over the GPUs")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "cp", "ring"],
+                    help="N > 1: dp = one G-buffer pass per GPU (weak scaling, default); cp = one video split over the GPUs with "
+                         "the Ulysses head exchange fused into the kernels; ring = the same split with the ring K/V schedule")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.workload.startswith("tokenizer"):

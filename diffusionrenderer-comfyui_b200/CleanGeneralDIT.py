@@ -275,6 +275,14 @@ class CleanGeneralDIT(nn.Module):
         }
         if cp is None:
             ws["attn"], ws["qkv"] = new(S, D), new(S, 3 * D)
+        elif cp.mode == "ring":
+            # every rank's [q | k | v] rows are visible to the others; remote K/V blocks land in two staging buffers of the
+            # same row pitch (only their k | v columns are written); fp32 running softmax state of the local query rows
+            ws["attn"] = new(S, D)
+            ws["qkv"], ws["qkv_peers"] = cp.alloc_views("qkv", (S, 3 * D))
+            ws["kv_stage"] = [new(S, 3 * D), new(S, 3 * D)]
+            ws["ring_o"] = new(S, D, dtype=torch.float32)
+            ws["ring_ml"] = new(S, self.num_heads, 2, dtype=torch.float32)
         else:
             ws["attn"], ws["attn_ptrs"] = cp.alloc("attn", (S, D))
             ws["a2a"], ws["a2a_ptrs"] = cp.alloc("a2a", (S * world, 3 * D // world))
@@ -327,12 +335,12 @@ class CleanGeneralDIT(nn.Module):
             if qkv is None:
                 qkv = ws["qkv"] = torch.empty(ws["S"], 3 * D, device=ws["x"].device, dtype=BF16)
             ops.gemm(ws["xm"], P["qkv"][i], out=qkv)
-            if cp is None:
+            if cp is None or cp.mode == "ring":
                 ops.qk_norm_rope(qkv, P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], self.num_heads)
             else:
                 ops.qk_norm_rope_scatter(qkv, P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], self.num_heads, ws["a2a_ptrs"],
                                          3 * D // cp.world, cp.rank * ws["S"])
-        elif cp is None:
+        elif cp is None or cp.mode == "ring":
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], out=ws["qkv"])
         else:
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], peer_ptrs=ws["a2a_ptrs"],
@@ -346,6 +354,8 @@ class CleanGeneralDIT(nn.Module):
         if cp is None:
             qkv = ws["qkv"]
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Hh, out=ws["attn"])
+        elif cp.mode == "ring":
+            self._ring_attention(ws)
         else:
             Dp, a2a = D // cp.world, ws["a2a"]
             ops.attention_cp(a2a[:, :Dp], a2a[:, Dp:2 * Dp], a2a[:, 2 * Dp:], Hh // cp.world, ws["attn_ptrs"], D, ws["S"],
@@ -353,6 +363,35 @@ class CleanGeneralDIT(nn.Module):
         if timers is not None:
             ev[1].record()
             timers.append(ev)
+
+    def _ring_attention(self, ws) -> None:
+        """Ring schedule over peer memory: block s of rank r is the K/V of rank (r - s) mod P.  While block s is attended
+        to on the current stream, block s + 1 is pulled from its owner's [q | k | v] buffer (k | v columns only) into the
+        other staging buffer on the copy stream; the attention kernel's ring epilogue merges the blocks."""
+        D, Hh, cp = self.model_channels, self.num_heads, ws["cp"]
+        P, r = cp.world, cp.rank
+        main, side = torch.cuda.current_stream(), cp.copy_stream
+        q = ws["qkv"][:, :D]
+        ready = torch.cuda.Event()
+        ready.record(main)                    # the barrier before this stage: every rank's K/V rows are in place
+        side.wait_event(ready)
+        copied, freed = {}, {}
+        for s in range(P):
+            if s + 1 < P:                     # prefetch the next block
+                nxt = ws["kv_stage"][(s + 1) & 1]
+                if (s - 1) in freed:          # the attention that read this staging buffer two steps ago must be done
+                    side.wait_event(freed[s - 1])
+                with torch.cuda.stream(side):
+                    nxt[:, D:].copy_(ws["qkv_peers"][(r - s - 1) % P][:, D:], non_blocking=True)
+                    copied[s + 1] = torch.cuda.Event()
+                    copied[s + 1].record(side)
+            kv = ws["qkv"] if s == 0 else ws["kv_stage"][s & 1]
+            if s > 0:
+                main.wait_event(copied[s])
+            ops.attention_ring_block(q, kv[:, D:2 * D], kv[:, 2 * D:], Hh, ws["ring_o"], ws["ring_ml"], first=(s == 0),
+                                     last=(s == P - 1), out=ws["attn"])
+            freed[s] = torch.cuda.Event()
+            freed[s].record(main)
 
     def stage_post_attention(self, ws, i: int, use_ca: bool) -> None:
         """out-projection with gated residual; cross-attention vector + AdaLN; MLP with gated residual"""

@@ -7,6 +7,15 @@ fused into the producing kernels as P2P stores over NVLink into peer-mapped buff
     qk_norm_rope_scatter  ->  [device barrier]  ->  attention over H/P heads x all S tokens, epilogue stores each output
     row to the GPU that owns the token  ->  [device barrier]  ->  out-projection on the local tokens
 
+Two exchange schemes share the plumbing (`mode`):
+  "ulysses" (default)  heads are split for the attention; the exchange is fused into the QKV GEMM epilogue and the
+                       attention epilogue as P2P stores (4 x S/P x D x 2 B per block and rank);
+  "ring"               heads stay whole, every rank keeps its query rows and visits the K/V blocks of all ranks in ring
+                       order (r, r-1, ...): the next block is pulled from its owner's memory over NVLink on a side stream
+                       while the current one is attended to, and the attention kernel's ring epilogue merges the blocks
+                       into an fp32 running state (2 x (P-1)/P x S x D x 2 B per block and rank — 3.5x the Ulysses traffic
+                       at P = 8, but no constraint that P divide the head count).
+
 torch.distributed (NCCL) is plumbing only: it carries the 64-byte CUDA IPC handles of the peer buffers at start-up and
 the final all-gather of the (tiny) latent.  `EmulatedGroup` runs the same kernels for P virtual ranks inside one process
 on one GPU (no barrier needed: the stages are issued rank after rank on one stream) — used by the single-GPU tests.
@@ -84,14 +93,16 @@ class PeerBuffer:
             _lib.check(_lib.load().drb_peer_import(raw, ctypes.byref(q)), "drb_peer_import")
             self.ptrs.append(q.value)
             self._imported.append(q.value)
-        self._holder = _RawTensor(self.local_ptr, nbytes)
-        self.bytes_tensor = torch.as_tensor(self._holder, device="cuda")
+        self._holders = [_RawTensor(p, nbytes) for p in self.ptrs]
+        self.peer_bytes = [torch.as_tensor(h, device="cuda") for h in self._holders]     # every rank's buffer, mapped here
+        self.bytes_tensor = self.peer_bytes[self.rank]
 
-    def view(self, shape, dtype) -> torch.Tensor:
+    def view(self, shape, dtype, rank: Optional[int] = None) -> torch.Tensor:
         n = 1
         for s in shape:
             n *= s
-        return self.bytes_tensor[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+        src = self.bytes_tensor if rank is None else self.peer_bytes[rank]
+        return src[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
 
     def close(self) -> None:
         lib = _lib.load()
@@ -106,10 +117,14 @@ class PeerBuffer:
 class ContextParallel:
     """Per-rank handle of a context-parallel group over torch.distributed (real multi-GPU)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, mode: str = "ulysses"):
         import torch.distributed as dist
+        if mode not in ("ulysses", "ring"):
+            raise ValueError("mode must be 'ulysses' or 'ring'")
         if not dist.is_initialized():
             raise RuntimeError("context parallelism needs an initialised torch.distributed process group (backend nccl)")
+        self.mode = mode
+        self.copy_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > _lib.CP_MAX_RANKS:
@@ -129,6 +144,12 @@ class ContextParallel:
                 old.close()
             self._buffers[name] = old = PeerBuffer(nbytes, self.group)
         return old.view(shape, dtype), list(old.ptrs)
+
+    def alloc_views(self, name: str, shape, dtype=BF16) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        """like alloc, but returns every rank's buffer as a tensor (P2P-mapped): what the ring pulls K/V blocks from"""
+        local, _ = self.alloc(name, shape, dtype)
+        buf = self._buffers[name]
+        return local, [buf.view(shape, dtype, r) for r in range(self.world)]
 
     def barrier(self) -> None:
         """device-side: enqueues one tiny kernel on the current stream; the host does not wait"""
@@ -151,9 +172,10 @@ class EmulatedGroup:
     no barrier (the caller issues every stage for all ranks before the next stage).  Test scaffolding for the sharding
     arithmetic and the two fused-exchange kernels; not a performance path."""
 
-    def __init__(self, world: int):
-        self.world = world
+    def __init__(self, world: int, mode: str = "ulysses"):
+        self.world, self.mode = world, mode
         self._tensors: Dict[str, List[torch.Tensor]] = {}
+        self.copy_stream = torch.cuda.Stream()
         self.ranks = [_EmulatedRank(self, r) for r in range(world)]
 
     def _alloc(self, name, shape, dtype):
@@ -165,7 +187,11 @@ class EmulatedGroup:
 
 class _EmulatedRank:
     def __init__(self, group: EmulatedGroup, rank: int):
-        self._g, self.rank, self.world = group, rank, group.world
+        self._g, self.rank, self.world, self.mode, self.copy_stream = group, rank, group.world, group.mode, group.copy_stream
+
+    def alloc_views(self, name: str, shape, dtype=BF16):
+        ts = self._g._alloc(name, shape, dtype)
+        return ts[self.rank], list(ts)
 
     def alloc(self, name: str, shape, dtype=BF16):
         ts = self._g._alloc(name, shape, dtype)

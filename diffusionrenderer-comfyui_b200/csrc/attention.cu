@@ -41,6 +41,12 @@ struct AttnParams {
   int64_t ld_o;
   int q_len, kv_len;
   int rows_per_rank, col0;
+  // ring form (drb_attention_bf16_ring): this launch is one K/V block of a longer key sequence.  The running state per
+  // (row, head) — reference m (log2 domain), sum l, un-normalised fp32 output — lives in ring_ml [q_len, H, 2] and ring_o
+  // [q_len, H*128]; the epilogue merges this block into it and, on the last block, writes the normalised bf16 rows.
+  float* ring_o;
+  float* ring_ml;
+  int ring_first, ring_last, num_heads;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -400,26 +406,74 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_wait(&s_full[t], n_kv & 1);
     tc_fence_after();
     const int row = q0 + t * kTileQ + quad * 32 + lane;
-    const float inv_l = 1.0f / l;
     __nv_bfloat16* dst = nullptr;
     if (row < p.q_len) {
       const int owner = row / p.rows_per_rank;
       dst = static_cast<__nv_bfloat16*>(p.o_peers[owner]) + static_cast<int64_t>(row - owner * p.rows_per_rank) * p.ld_o + p.col0 +
             head * kHeadDim;
     }
+    if (p.ring_o == nullptr) {
+      const float inv_l = 1.0f / l;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t o[32];
-      tmem_ld32(o_tmem + c * 32, o);
-      tmem_wait_ld();
-      if (row < p.q_len) {
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(o_tmem + c * 32, o);
+        tmem_wait_ld();
+        if (row < p.q_len) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            w[i] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * i]) * inv_l, __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int i = 0; i < 4; ++i)
+              w[i] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * i]) * inv_l, __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    } else {
+      // merge this K/V block into the running state: m' = max(m, M); O' = O 2^(m-m') + O_blk 2^(M-m'); l likewise
+      const bool ok = row < p.q_len;
+      const int64_t rh = static_cast<int64_t>(ok ? row : 0) * p.num_heads + head;
+      float m_old = -INFINITY, l_old = 0.f;
+      if (!p.ring_first && ok) {
+        const float2 ml = *reinterpret_cast<const float2*>(p.ring_ml + 2 * rh);
+        m_old = ml.x;
+        l_old = ml.y;
+      }
+      const float m_new = fmaxf(m_old, M);
+      const float a = p.ring_first ? 0.f : ex2(m_old - m_new), b = ex2(M - m_new);
+      const float l_new = l_old * a + l * b;
+      const float inv_l = 1.0f / l_new;
+      float* so = p.ring_o + rh * kHeadDim;
+      if (!p.ring_last && ok) *reinterpret_cast<float2*>(p.ring_ml + 2 * rh) = make_float2(m_new, l_new);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(o_tmem + c * 32, o);
+        tmem_wait_ld();
+        if (!ok) continue;
+        float v[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!p.ring_first) prev = *reinterpret_cast<const float4*>(so + c * 32 + g * 4);
+          v[g * 4 + 0] = prev.x * a + __uint_as_float(o[g * 4 + 0]) * b;
+          v[g * 4 + 1] = prev.y * a + __uint_as_float(o[g * 4 + 1]) * b;
+          v[g * 4 + 2] = prev.z * a + __uint_as_float(o[g * 4 + 2]) * b;
+          v[g * 4 + 3] = prev.w * a + __uint_as_float(o[g * 4 + 3]) * b;
+        }
+        if (p.ring_last) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = pack_bf16x2(v[g * 8 + 2 * i] * inv_l, v[g * 8 + 2 * i + 1] * inv_l);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(so + c * 32 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
         }
       }
     }
@@ -439,7 +493,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }  // namespace drb
 
 static int attention_launch(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
-                            int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0, void* stream) {
+                            int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0, void* stream,
+                            float* ring_o = nullptr, float* ring_ml = nullptr, int ring_first = 0, int ring_last = 0) {
   using namespace drb;
   DRB_REQUIRE(q && k && v && o_peers, "null pointer");
   DRB_REQUIRE(q_len > 0 && kv_len > 0 && num_heads > 0, "q_len, kv_len, num_heads must be positive");
@@ -458,6 +513,11 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
   p.kv_len = kv_len;
   p.rows_per_rank = rows_per_rank;
   p.col0 = col0;
+  p.ring_o = ring_o;
+  p.ring_ml = ring_ml;
+  p.ring_first = ring_first;
+  p.ring_last = ring_last;
+  p.num_heads = num_heads;
   CUtensorMap tq, tk, tv;
   const uint64_t cols = static_cast<uint64_t>(num_heads) * kHeadDim;
   int rc = make_tmap_2d_bf16(&tq, q, q_len, cols, ld_qkv, kTileQ, 64);
@@ -504,6 +564,18 @@ extern "C" int drb_attention_bf16_cp(const void* q, const void* k, const void* v
                                      int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0,
                                      void* stream) {
   return attention_launch(q, k, v, ld_qkv, o_peers, world, ld_o, q_len, kv_len, num_heads, rows_per_rank, col0, stream);
+}
+
+extern "C" int drb_attention_bf16_ring(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                                       float* state_o, float* state_ml, int q_len, int kv_len, int num_heads, int first, int last,
+                                       void* stream) {
+  using namespace drb;
+  DRB_REQUIRE(state_o && state_ml, "ring attention needs the running-state buffers");
+  DRB_REQUIRE((reinterpret_cast<uintptr_t>(state_o) & 15) == 0 && (reinterpret_cast<uintptr_t>(state_ml) & 7) == 0, "state buffers misaligned");
+  DRB_REQUIRE(!last || o != nullptr, "the last block writes the output");
+  void* peers[1] = {o ? o : static_cast<void*>(state_o)};
+  return attention_launch(q, k, v, ld_qkv, peers, 1, o ? ld_o : static_cast<int64_t>(num_heads) * kHeadDim, q_len, kv_len, num_heads,
+                          0x7fffffff, 0, stream, state_o, state_ml, first ? 1 : 0, last ? 1 : 0);
 }
 
 #ifdef DRB_ATTN_PROFILE

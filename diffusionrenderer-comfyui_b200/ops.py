@@ -400,3 +400,24 @@ def qkv_gemm_norm_rope(a: torch.Tensor, w: torch.Tensor, wq: torch.Tensor, wk: t
               wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), _lib.ptr_array(peer_ptrs), len(peer_ptrs),
               peer_ld, row0, _stream())
     return None
+
+
+def attention_ring_block(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, state_o: torch.Tensor,
+                         state_ml: torch.Tensor, first: bool, last: bool, out: Optional[torch.Tensor] = None) -> None:
+    """one K/V block of ring attention: merges softmax(q k^T) v over this block into the fp32 running state; the last block
+    writes the normalised rows to `out` [q_len, H*128]"""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, n)
+    _req(state_o, "state_o", torch.float32), _req(state_ml, "state_ml", torch.float32)
+    ld = _rows2d(q, "q")
+    if _rows2d(k, "k") != ld or _rows2d(v, "v") != ld:
+        raise ValueError("q, k, v must share one row pitch")
+    if state_o.numel() != q.shape[0] * num_heads * 128 or state_ml.numel() != q.shape[0] * num_heads * 2:
+        raise ValueError("state buffers do not match q_len x heads")
+    if last:
+        if out is None:
+            raise ValueError("the last block needs `out`")
+        _req(out, "out")
+    _lib.call("drb_attention_bf16_ring", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _ptr(out) if last else None,
+              _rows2d(out, "out") if last else 0, state_o.data_ptr(), state_ml.data_ptr(), q.shape[0], k.shape[0], num_heads,
+              int(first), int(last), _stream())

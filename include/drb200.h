@@ -50,6 +50,14 @@ int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int M, int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
                   int cta_group, void* stream);
 
+/* Ring form (context parallelism when heads are not split: every GPU keeps its query rows and visits the K/V blocks of
+ * all GPUs in ring order): one launch = one K/V block.  Running state per (row, head): state_ml [q_len, H, 2] fp32 =
+ * (reference in log2 units, row sum), state_o [q_len, H*128] fp32 = un-normalised output.  `first` initialises the state,
+ * every launch merges its block into it (m' = max(m, M); O' = O 2^(m-m') + O_blk 2^(M-m'); l likewise), `last` writes the
+ * normalised bf16 rows to o [q_len, ld_o] instead of the state.  Same kernel, other epilogue. */
+int drb_attention_bf16_ring(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o, float* state_o,
+                            float* state_ml, int q_len, int kv_len, int num_heads, int first, int last, void* stream);
+
 /* Fused QKV projection: [q | k | v] = A[M,K] @ W[3D,K]^T with, in the epilogue, per-head RMSNorm of q and k (weights
  * wq, wk [128], eps 1e-6) and RoPE from the bf16 tables cos_tab / sin_tab [M,128] — i.e. drb_gemm_bf16 followed by
  * drb_qk_norm_rope without the round trip of q and k through HBM (CleanGeneralDIT.py:268-297).  world == 0: rows are

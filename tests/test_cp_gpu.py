@@ -20,6 +20,82 @@ DEV = "cuda"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_ring_blocks_merge_to_the_full_attention():
+    """drb_attention_bf16_ring over K/V blocks of uneven length == one attention over all keys (fp32 running state)"""
+    import torch.nn.functional as F
+    from drb200 import ops
+    from tests.util import rel_l2
+    g = torch.Generator(device=DEV).manual_seed(9)
+    Sq, H = 300, 2
+    blocks = [130, 257, 64, 500]                                  # ragged tiles inside blocks; logits grow along the sequence
+    Skv = sum(blocks)
+    q = torch.randn(Sq, H * 128, device=DEV, generator=g).bfloat16()
+    k = (torch.randn(Skv, H * 128, device=DEV, generator=g) * torch.linspace(0.3, 3.0, Skv, device=DEV)[:, None]).bfloat16()
+    v = torch.randn(Skv, H * 128, device=DEV, generator=g).bfloat16()
+    st_o = torch.empty(Sq, H * 128, device=DEV, dtype=torch.float32)
+    st_ml = torch.empty(Sq, H, 2, device=DEV, dtype=torch.float32)
+    out = torch.empty(Sq, H * 128, device=DEV, dtype=torch.bfloat16)
+    start = 0
+    for i, n in enumerate(blocks):
+        ops.attention_ring_block(q, k[start:start + n], v[start:start + n], H, st_o, st_ml, first=(i == 0), last=(i == len(blocks) - 1),
+                                 out=out)
+        start += n
+    ref = F.scaled_dot_product_attention(*(t.float().reshape(-1, H, 128).permute(1, 0, 2)[None] for t in (q, k, v)))[0]
+    ref = ref.permute(1, 0, 2).reshape(Sq, H * 128)
+    assert rel_l2(out, ref) <= 5e-3
+    assert rel_l2(out, ops.attention(q, k, v, H)) <= 4e-3
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_emulated_ring_matches_one_gpu(world):
+    """ring mode (heads whole, K/V blocks pulled from the other ranks' buffers): same forward up to the order in which the
+    key blocks enter the softmax"""
+    from drb200 import ops
+    from drb200.context_parallel import EmulatedGroup, shard_frames
+    from tests.util import rel_l2
+    dims = TINY_INVERSE
+    model, _ = build_product_model(dims, "inverse", seed=3)
+    net = model.net
+    T, H, W = 4, 12, 20
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(1, 16, T, H, W, device=DEV, generator=g).bfloat16()
+    cond = (torch.randn(1, 16, T, H, W, device=DEV, generator=g) * 0.5).bfloat16()
+    ci = torch.full((1, 1), 2, dtype=torch.long, device=DEV)
+    sigma = torch.tensor(1.26, device=DEV)
+    with torch.no_grad():
+        ref = net(x=x, timesteps=sigma, latent_condition=cond, context_index=ci)
+        group = EmulatedGroup(world, mode="ring")
+        wss, outs = [], []
+        for cp in group.ranks:
+            t0, t1 = shard_frames(T, cp.rank, world)
+            ws = net._workspace(t1 - t0, H, W, x.device, cp)
+            ws["sigma"].copy_(sigma.reshape(1))
+            net.modulation(ws, ws["sigma"])
+            net.prepare_condition(ws, cond[:, :, t0:t1], t1 - t0, H, W)
+            ops.patchify_condition(x[0, :, t0:t1].contiguous(), ws["tok"], 0, t1 - t0, H, W)
+            use_ca = net.prepare_context(ws, net.context_token(ci))
+            net.stage_embed(ws)
+            wss.append(ws)
+        for i in range(net.num_blocks):
+            for ws in wss:
+                net.stage_pre_attention(ws, i)
+            torch.cuda.synchronize()            # stands in for the device barrier (the ring uses a second stream)
+            for ws in wss:
+                net.stage_attention(ws, i)
+            torch.cuda.synchronize()
+            for ws in wss:
+                net.stage_post_attention(ws, i, use_ca)
+        for cp, ws in zip(group.ranks, wss):
+            t0, t1 = shard_frames(T, cp.rank, world)
+            out = torch.empty((16, t1 - t0, H, W), device=DEV, dtype=torch.bfloat16)
+            ops.unpatchify_euler(net.stage_final(ws), None, 0.0, None, None, None, None, f_out=out)
+            outs.append(out)
+    got = torch.cat(outs, dim=1).unsqueeze(0)
+    err = rel_l2(got, ref)
+    print(f"\nring P={world}: F rel-L2 vs one GPU {err:.3e}")
+    assert err <= 6e-3
+
+
 @pytest.mark.parametrize("dims,mt", [(TINY_INVERSE, "inverse"), (TINY_FORWARD, "forward")])
 @pytest.mark.parametrize("world", [2, 4])
 def test_emulated_ranks_are_bit_identical_to_one_gpu(dims, mt, world):

@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--ring", action="store_true", help="ring K/V schedule instead of the Ulysses head exchange")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -23,7 +24,8 @@ def main():
     from drb200 import diffusion_renderer_config as cfgm
     from drb200.context_parallel import ContextParallel
     from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
-    cp = ContextParallel()
+    cp = ContextParallel(mode="ring" if args.ring else "ulysses")
+    from tests.util import rel_l2
     ok = True
     if args.tiny:
         cfg = cfgm.get_inverse_renderer_config(64, 96, 9)
@@ -52,9 +54,14 @@ def main():
             ref_g = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci},
                                         {"latent_condition": torch.zeros_like(cond), "context_index": torch.zeros_like(ci)}, guidance=2.0)
         torch.cuda.synchronize()
-        e = [bool(torch.equal(got, ref)), bool(torch.equal(got_z, ref_z)), bool(torch.equal(got_g, ref_g))]
-        print(f"rank {rank}/{world}: forward identical={e[0]} sampler identical={e[1]} cfg sampler identical={e[2]}", flush=True)
-        ok = all(e)
+        if args.ring:      # the key blocks enter the softmax in another order: equal up to rounding, not bit-identical
+            errs = [rel_l2(got, ref), rel_l2(got_z, ref_z), rel_l2(got_g, ref_g)]
+            print(f"rank {rank}/{world}: ring forward rel-L2 {errs[0]:.2e} sampler {errs[1]:.2e} cfg sampler {errs[2]:.2e}", flush=True)
+            ok = errs[0] <= 6e-3 and errs[1] <= 1e-2 and errs[2] <= 1e-2
+        else:
+            e = [bool(torch.equal(got, ref)), bool(torch.equal(got_z, ref_z)), bool(torch.equal(got_g, ref_g))]
+            print(f"rank {rank}/{world}: forward identical={e[0]} sampler identical={e[1]} cfg sampler identical={e[2]}", flush=True)
+            ok = all(e)
     if args.full:
         cfg = cfgm.get_inverse_renderer_config(704, 1280, 57)
         cfg["model_type"] = "inverse"
@@ -74,7 +81,7 @@ def main():
         x = (torch.randn(16, T, H, W, device=dev, generator=g).bfloat16() * sig[0]).bfloat16()[:, rank * Tl:(rank + 1) * Tl].contiguous()
         net.prepare_condition(ws, cond[:, :, rank * Tl:(rank + 1) * Tl], Tl, H, W)
         use_ca = net.prepare_context(ws, net.context_token(torch.zeros(1, 1, dtype=torch.long, device=dev)))
-        for fused in (True, False, True, False):
+        for fused in ((True,) if args.ring else (True, False, True, False)):
             net.fuse_qkv_epilogue = fused
             for i in range(3):
                 net.denoise_step(ws, x, sig[i:i + 1], sig[i + 1:i + 2], use_ca)
@@ -91,7 +98,8 @@ def main():
             ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print(f"CP{world} 7B denoise step 57x704x1280, QKV all-to-all {'in the GEMM epilogue' if fused else 'as a scatter kernel'}: "
+                what = "ring K/V schedule over peer memory" if args.ring else f"QKV all-to-all {'in the GEMM epilogue' if fused else 'as a scatter kernel'}"
+                print(f"CP{world} 7B denoise step 57x704x1280, {what}: "
                       f"{ms.item():.1f} ms/step (max over ranks), finite={bool(torch.isfinite(x.float()).all())}", flush=True)
         net.fuse_qkv_epilogue = True
     flag = torch.tensor([1 if ok else 0], device=dev)
