@@ -17,4 +17,7 @@ Parity status
   ``diffusers.AutoencoderKLCosmos`` (diffusers >= 0.34, not installed, not
   vendored); the restatement follows ``VAE_config.json`` + SURVEY Appendix B and
   is only self-checked (shapes, causality, Haar round trip, parameter count).
+* ``envmap_oracle``: the torch stages of ``preprocess_envmap.py`` are PINNED bit-for-bit against the reference's own
+  functions (imported with stubbed nvdiffrast / imageio / cv2); the cube-map fetch (``nvdiffrast.torch.texture``) is
+  **parity unpinned** and self-checked (texel-centre exactness, seamlessness).
 """
