@@ -217,16 +217,17 @@ def random_tokenizer(torch, dev):
     return vae
 
 
-def time_video(torch, dist, model, wl, rank, world, dev):
-    """One inverse-rendered video through the pipeline API, dp over G-buffer passes: returns (seconds max over ranks,
-    passes of this rank, h2d bytes, d2h bytes)."""
+def time_video(torch, dist, model, wl, rank, world, dev, cp_mode=False):
+    """One inverse-rendered video through the pipeline API: dp = the five G-buffer passes dealt over the ranks; cp = every
+    rank runs all five passes, each pass's token sequence split over the ranks (the tokenizer runs replicated).  Returns
+    (seconds max over ranks, passes of this rank, h2d bytes, d2h bytes)."""
     from drb200.diffusion_renderer_pipeline import CleanDiffusionRendererPipeline
     f, hh, ww = wl["clip"]
     vae = random_tokenizer(torch, dev)
     pipe = CleanDiffusionRendererPipeline(checkpoint_dir="", checkpoint_name="", model_type="inverse", vae_instance=vae,
                                           model_instance=model, guidance=0.0, num_steps=15, seed=42)
     clip = (torch.rand(1, 3, f, hh, ww, generator=torch.Generator().manual_seed(1234)) * 2 - 1).pin_memory()   # host, fp32
-    mine = [p for p in range(5) if p % world == rank]
+    mine = list(range(5)) if cp_mode else [p for p in range(5) if p % world == rank]
 
     def render(passes, steps):
         pipe.num_steps = steps
@@ -361,10 +362,9 @@ def run_b200(args, wl):
     d2h = hout.numel() * 2
 
     video = None
-    if not args.no_video and not cp_mode:
-        net.enable_context_parallel(None)
-        v_s, v_passes, v_h2d, v_d2h = time_video(torch, dist, model, wl, rank, world, dev)
-        video = {"s_per_video": v_s, "passes_per_rank": -(-5 // world), "passes_rank0": v_passes, "steps_per_pass": 15,
+    if not args.no_video:
+        v_s, v_passes, v_h2d, v_d2h = time_video(torch, dist, model, wl, rank, world, dev, cp_mode)
+        video = {"s_per_video": v_s, "passes_per_rank": 5 if cp_mode else -(-5 // world), "passes_rank0": v_passes, "steps_per_pass": 15,
                  "h2d_bytes_rank0": v_h2d, "d2h_bytes_rank0": v_d2h,
                  "api": "CleanDiffusionRendererPipeline.generate_video per G-buffer pass (host fp32 clip in, host uint8 frames out), "
                         "tokenizer encode once + 15 Euler steps + decode + post-process per pass; random-init tokenizer"}

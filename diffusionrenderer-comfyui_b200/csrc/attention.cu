@@ -527,15 +527,15 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
   rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, kTileKV, 64);
   if (rc) return rc;
   // fraction of the exponentials computed on the FMA pipe; DRB_ATTN_POLY (0 -> 0/16, 1 -> 4/16, 2 -> 5/16, 3 -> 8/16,
-  // 4 -> 3/16, 5 -> 2/16) is a tuning switch only, the default is what was measured fastest on B200.
+  // 4 -> 3/16, 5 -> 2/16, 6 -> 6/16, 7 -> 7/16) is a tuning switch only, the default is what was measured fastest on B200.
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("DRB_ATTN_POLY");
     variant = e ? atoi(e) : 2;
-    if (variant < 0 || variant > 5) variant = 2;
+    if (variant < 0 || variant > 7) variant = 2;
 #define DRB_ATTN_CFG(mask) \
     DRB_CUDA(cudaFuncSetAttribute(attention_kernel<mask>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    DRB_ATTN_CFG(0x0000u) DRB_ATTN_CFG(0x1111u) DRB_ATTN_CFG(0x4924u) DRB_ATTN_CFG(0x5555u) DRB_ATTN_CFG(0x0421u) DRB_ATTN_CFG(0x0101u)
+    DRB_ATTN_CFG(0x0000u) DRB_ATTN_CFG(0x1111u) DRB_ATTN_CFG(0x4924u) DRB_ATTN_CFG(0x5555u) DRB_ATTN_CFG(0x0421u) DRB_ATTN_CFG(0x0101u) DRB_ATTN_CFG(0x2929u) DRB_ATTN_CFG(0x52A5u)
 #undef DRB_ATTN_CFG
   }
   dim3 grid((q_len + kTileQ * kQTilesPerCta - 1) / (kTileQ * kQTilesPerCta), num_heads);
@@ -547,6 +547,8 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
     case 3: DRB_ATTN_LAUNCH(0x5555u) break;
     case 4: DRB_ATTN_LAUNCH(0x0421u) break;
     case 5: DRB_ATTN_LAUNCH(0x0101u) break;
+    case 6: DRB_ATTN_LAUNCH(0x2929u) break;
+    case 7: DRB_ATTN_LAUNCH(0x52A5u) break;
     default: DRB_ATTN_LAUNCH(0x4924u) break;
   }
 #undef DRB_ATTN_LAUNCH
