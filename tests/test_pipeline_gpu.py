@@ -148,3 +148,29 @@ def test_inverse_node_returns_five_gbuffers(monkeypatch):
         ref = so.postprocess(video_ref, name == "normal")[0]
         assert psnr_u8((out.numpy() * 255).round().astype(np.uint8), ref) >= 40.0
     assert not torch.equal(outs[0], outs[1])          # the passes differ through the context embedding
+
+
+def test_single_image_path_matches_oracle_chain():
+    """T = 1 (a ComfyUI IMAGE of one frame): tokenizer image path, one latent frame through the DiT, decode to one frame"""
+    vae, vsd = _vae()
+    steps, thw = 2, (1, 64, 96)
+    pipe, model, sdn = _pipeline(MICRO_INVERSE, "inverse", vae, steps)
+    clip = (torch.rand(1, 3, *thw, device=DEV, generator=torch.Generator(device=DEV).manual_seed(11)) * 2 - 1)
+    ci = torch.full((1, 1), 0, dtype=torch.long, device=DEV)
+    got = pipe.generate_video({"rgb": clip, "video": clip, "context_index": ci}, seed=3)
+    _, video_ref = _oracle_video(sdn, MICRO_INVERSE, vsd, {"rgb": clip.bfloat16()}, ["rgb"], False, ci, steps, 3, thw)
+    assert got.shape == (1, 1, 64, 96, 3)
+    assert psnr_u8(got, so.postprocess(video_ref)) >= 40.0
+
+
+def test_batched_clips_are_rejected_like_the_reference():
+    """the reference sampler is batch-1 (model_diffusion_renderer.py:222): B > 1 must fail loudly, not silently
+    render the first clip"""
+    vae, _ = _vae()
+    pipe, model, _ = _pipeline(MICRO_INVERSE, "inverse", vae, 2)
+    clip = torch.rand(2, 3, 9, 32, 48, device=DEV) * 2 - 1
+    ci = torch.zeros(2, 1, dtype=torch.long, device=DEV)
+    with pytest.raises((ValueError, RuntimeError)):
+        pipe.generate_video({"rgb": clip, "video": clip, "context_index": ci}, seed=3)
+    with pytest.raises(ValueError):
+        pipe.generate_video({"context_index": ci})                      # no tensor to infer the clip shape from
