@@ -35,7 +35,9 @@ def assert_close_bf16(got, ref, max_ulp=1, min_exact=0.98):
 
 
 @pytest.mark.parametrize("cg", [1, 2])
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 520, 136), (48, 64, 256), (1000, 768, 616), (2048, 512, 2048)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 520, 136), (48, 64, 256), (1000, 768, 616), (2048, 512, 2048),
+                                   (3520, 4096, 256),    # a context-parallel shard (ragged last m-tile)
+                                   (3520, 1152, 136)])
 def test_gemm_store(cg, M, N, K):
     from drb200 import ops
     g = gen(1)
@@ -228,7 +230,7 @@ def test_postprocess_u8(normalize):
     assert (diff == 0).mean() >= 0.97
 
 
-@pytest.mark.parametrize("M,D,K", [(300, 256, 256), (1000, 512, 512), (77, 256, 136)])
+@pytest.mark.parametrize("M,D,K", [(300, 256, 256), (1000, 512, 512), (77, 256, 136), (3520, 1024, 256)])
 def test_fused_qkv_gemm_norm_rope_matches_the_unfused_kernels(M, D, K):
     """drb_gemm_qkv_norm_rope == drb_gemm_bf16 followed by drb_qk_norm_rope, up to the summation order of the RMS"""
     from drb200 import ops
