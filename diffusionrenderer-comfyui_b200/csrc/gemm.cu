@@ -14,6 +14,7 @@
 //
 // Roofline: tensor pipe.  Algorithmic work = 2*M*N*K flop per launch.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/drb200.h"
 #include "common.cuh"
@@ -27,7 +28,7 @@ constexpr int kBlockN = 256;   // columns of the output tile (rows of W)
 constexpr int kBlockK = 64;    // one 128-byte swizzle atom of bf16
 constexpr int kUmmaK = 16;
 constexpr int kNumThreads = 256;
-constexpr int kBandTilesN = 16;  // rasterisation: bands of 16 n-tiles keep the W band (<= 32 MB at K=4096) in L2
+constexpr int kMaxBandTilesN = 16;   // rasterisation: bands of <= 16 n-tiles whose W rows (band * 256 * K * 2 B) stay in L2
 
 template <int kCtaGroup>
 struct GemmCfg {
@@ -44,6 +45,7 @@ struct GemmCfg {
 
 struct GemmParams {
   int M, N, K;
+  int band;      // n-tiles per rasterisation band
   __nv_bfloat16* out;
   int64_t ldo;
   const __nv_bfloat16* resid;
@@ -61,12 +63,12 @@ struct GemmParams {
   void* peers[DRB_CP_MAX_RANKS];
 };
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& m, int& n) {
-  const int per_band = tiles_m * kBandTilesN;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int band_n, int& m, int& n) {
+  const int per_band = tiles_m * band_n;
   const int band = t / per_band;
   const int r = t - band * per_band;
-  const int n0 = band * kBandTilesN;
-  const int w = min(kBandTilesN, tiles_n - n0);
+  const int n0 = band * band_n;
+  const int w = min(band_n, tiles_n - n0);
   m = r / w;
   n = n0 + (r - m * w);
 }
@@ -132,7 +134,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int tm, tn;
-        tile_coords(t, tiles_m, tiles_n, tm, tn);
+        tile_coords(t, tiles_m, tiles_n, p.band, tm, tn);
         const int row_a = tm * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
         const int row_b = tn * kBlockN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -203,7 +205,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int iter = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
       int tm, tn;
-      tile_coords(t, tiles_m, tiles_n, tm, tn);
+      tile_coords(t, tiles_m, tiles_n, p.band, tm, tn);
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       mbar_wait(&tmem_full_bar[as], aphase);
@@ -402,6 +404,21 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   return 0;
 }
 
+// n-tiles per band: the W rows of a band (256 * K * 2 B per n-tile) should sit in L2 (126 MB) next to the streaming A rows
+int pick_band(int K) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("DRB_GEMM_BAND");      // tuning runs only
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+  const int64_t per_tile = 256LL * K * 2;
+  int band = static_cast<int>((64LL << 20) / per_tile);   // K = 16384 -> 8 (measured best: 1511 vs 1487 TF/s at 16), K <= 8192 -> 16
+  if (band < 1) band = 1;
+  if (band > kMaxBandTilesN) band = kMaxBandTilesN;
+  return band;
+}
+
 template <int kCtaGroup>
 int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
   switch (epi) {
@@ -441,6 +458,7 @@ extern "C" int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   if (rc) return rc;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
+  p.band = pick_band(K);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.resid = static_cast<const __nv_bfloat16*>(resid);
@@ -461,6 +479,7 @@ extern "C" int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W,
                 reinterpret_cast<uintptr_t>(sin_tab)) & 15) == 0, "norm weights / RoPE tables must be 16-byte aligned");
   GemmParams p{};
   p.M = M; p.N = 3 * D; p.K = K;
+  p.band = pick_band(K);
   p.wq = static_cast<const __nv_bfloat16*>(wq);
   p.wk = static_cast<const __nv_bfloat16*>(wk);
   p.cos_tab = static_cast<const __nv_bfloat16*>(cos_tab);
