@@ -82,3 +82,39 @@ def test_full_size_forward_is_deterministic_and_euler_is_linear_in_f(full_model)
     x0, x1, x2 = st(torch.zeros_like(f)), st(f), st(2 * f)
     ulp = 2.0 ** -7 * torch.maximum(torch.maximum(x0.abs(), x1.abs()), x2.abs()).clamp_min(2.0 ** -6)
     assert ((x2 - x1) - (x1 - x0)).abs().le(2.0 * ulp).all()
+
+
+def test_full_size_tokenizer_matches_oracle():
+    """CV8x8x8 tokenizer at the bench clip size (57 x 704 x 1280, full channel widths): encode and decode against the oracle
+    in fp32 and in bf16 on the same GPU — the product may be no further from fp32 than 2x the bf16 oracle's own error."""
+    if torch.cuda.get_device_properties(0).total_memory < 60 * 2 ** 30:
+        pytest.skip("needs ~40 GiB of device memory")
+    from oracle import vae_oracle as vo
+    from drb200.CleanVAE import AutoencoderKLCosmos, CleanVAE
+    sd = vo.make_vae_state_dict(vo.FULL_VAE, seed=11)
+    model = AutoencoderKLCosmos()
+    model.load_state_dict(sd, strict=True)
+    vae = CleanVAE(model=model)
+    vae.to(DEV)
+    vae.reset_dtype(torch.bfloat16)
+    sd16 = {k: v.to(DEV).bfloat16() for k, v in sd.items()}
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    x = (torch.rand(1, 3, 57, 704, 1280, device=DEV, generator=torch.Generator(device=DEV).manual_seed(21)) * 2 - 1).bfloat16()
+    with torch.no_grad():
+        z = vae.encode(x)
+        z16 = vo.encode(sd16, vo.FULL_VAE, x)
+        z32 = vo.encode(sd32, vo.FULL_VAE, x.float())
+        floor, err = rel_l2(z16, z32), rel_l2(z, z32)
+        print(f"\nfull-size encode: product-vs-fp32 {err:.3e}   bf16-oracle-vs-fp32 {floor:.3e}")
+        assert z.shape == (1, 16, 8, 88, 160)
+        assert err <= 2 * floor + 2e-3
+        zin = z32.bfloat16()
+        del z16, z32
+        torch.cuda.empty_cache()
+        y = vae.decode(zin)
+        y16 = vo.decode(sd16, vo.FULL_VAE, zin)
+        y32 = vo.decode(sd32, vo.FULL_VAE, zin.float())
+        floor, err = rel_l2(y16, y32), rel_l2(y, y32)
+        print(f"full-size decode: product-vs-fp32 {err:.3e}   bf16-oracle-vs-fp32 {floor:.3e}")
+        assert y.shape == (1, 3, 57, 704, 1280)
+        assert err <= 2 * floor + 2e-3
