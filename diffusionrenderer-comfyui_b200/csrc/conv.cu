@@ -39,7 +39,8 @@ constexpr int kABytes = 128 * kBlockK * 2;      // 16 KB
 constexpr int kBBytes = kMaxN * kBlockK * 2;    // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kStages = 4;
-constexpr int kConvSmem = kStages * kStageBytes + 1024 + 256;
+constexpr int kEpiStage = 4 * 2048;             // per epilogue warp: 32 pixels x 64 B (one 32-channel chunk), XOR-swizzled
+constexpr int kConvSmem = kStages * kStageBytes + 1024 + 256 + kEpiStage;
 constexpr int kConvThreads = 256;
 
 struct ConvMaps {
@@ -77,6 +78,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_stage = smem + kStages * kStageBytes + 256;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -247,11 +249,10 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         uint32_t acc[32];
         tmem_ld32(taddr + c * 32, acc);
         tmem_wait_ld();
-        if (!ok) continue;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int cg = col + g * 8;
-          if (cg >= p.Cout || c * 32 + g * 8 >= p.block_n) continue;
+          if (!ok || cg >= p.Cout || c * 32 + g * 8 >= p.block_n) continue;   // (all lanes meet again at the __syncwarp below)
           float v[8];
           const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
           const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -285,8 +286,21 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             s1 += a + b;
             s2 += a * a + b * b;
           }
-          *reinterpret_cast<uint4*>(orow + cg) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(epi_stage + q * 2048 + lane * 64 + ((g ^ ((lane >> 1) & 3)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
+        // this warp's 32 pixels are two rows of 16 consecutive pixels: store 64-byte channel segments, 8 pixels per instruction
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), ch = lane & 3;
+          const int ph = h0 + (q * 32 + rr) / kTileW, pw = w0 + (q * 32 + rr) % kTileW;
+          if (ph < p.H_out && pw < p.W_out && col + ch * 8 < p.Cout && c * 32 + ch * 8 < p.block_n) {
+            const int64_t px = (static_cast<int64_t>(t) * p.out_H + ph * p.out_scale + p.out_off_h) * p.out_W + pw * p.out_scale + p.out_off_w;
+            *reinterpret_cast<uint4*>(p.out + px * p.Cout + col + ch * 8) =
+                *reinterpret_cast<const uint4*>(epi_stage + q * 2048 + rr * 64 + ((ch ^ ((rr >> 1) & 3)) * 16));
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

@@ -46,6 +46,7 @@ struct GemmCfg {
 struct GemmParams {
   int M, N, K;
   int band;      // n-tiles per rasterisation band
+  int stage_out; // generic epilogues: stage each 32-column chunk through shared memory and store 64-byte row segments
   __nv_bfloat16* out;
   int64_t ldo;
   const __nv_bfloat16* resid;
@@ -348,7 +349,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               o[j] = pack_bf16x2(bf16_lo(rr[j]) + t0, bf16_hi(rr[j]) + t1);
             }
           }
-          *reinterpret_cast<uint4*>(out_row + cg) = make_uint4(o[0], o[1], o[2], o[3]);
+          if (p.stage_out)
+            *reinterpret_cast<uint4*>(epi_stage + q * 2048 + lane * 64 + ((g ^ ((lane >> 1) & 3)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+          else
+            *reinterpret_cast<uint4*>(out_row + cg) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (p.stage_out) {
+          // rows of this warp, 64 bytes (32 columns) each: 8 rows per store instruction, 4 lanes per row
+          __syncwarp();
+          const int row_base = row - lane;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), ch = lane & 3;
+            if (row_base + rr < p.M && col + ch * 8 < p.N)
+              *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(row_base + rr) * p.ldo + col + ch * 8) =
+                  *reinterpret_cast<const uint4*>(epi_stage + q * 2048 + rr * 64 + ((ch ^ ((rr >> 1) & 3)) * 16));
+          }
+          __syncwarp();
         }
       }
       }
@@ -376,7 +393,7 @@ template <int kCtaGroup, int kEpi>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kCtaGroup>;
   auto kernel = gemm_bf16_kernel<kCtaGroup, kEpi>;
-  constexpr int kSmem = Cfg::kSmemBytes + (kEpi == DRB_EPI_QKV_NORM_ROPE ? Cfg::kEpiStageBytes : 0);
+  constexpr int kSmem = Cfg::kSmemBytes + (kEpi == DRB_EPI_QKV_NORM_ROPE ? Cfg::kEpiStageBytes : 4 * 2048);
   static_assert(kSmem <= 232448, "over the 227 KB shared-memory limit of sm_100");
   static bool configured = false;   // per template instance
   if (!configured) {
@@ -459,6 +476,14 @@ extern "C" int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.band = pick_band(K);
+  {
+    static int stage = -1;
+    if (stage < 0) {
+      const char* e = getenv("DRB_GEMM_STAGE");   // tuning runs only
+      stage = e ? atoi(e) : 1;
+    }
+    p.stage_out = stage;
+  }
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.resid = static_cast<const __nv_bfloat16*>(resid);
