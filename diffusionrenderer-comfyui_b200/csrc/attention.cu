@@ -142,7 +142,10 @@ __device__ unsigned long long g_attn_prof[16];
 #define PROF_DUMP(base)
 #endif
 
-template <uint32_t kPolyMask>
+// kPair: the two CTAs of a cluster work on adjacent query blocks of the same head and need the same K/V tiles in the same
+// order: each loads half of every tile (64 rows) and TMA multicasts it into both CTAs, halving the L2 -> SM traffic; a ring
+// slot is reused only after the MMAs of BOTH CTAs have released it (multicast tcgen05.commit on a 2-arrival barrier).
+template <uint32_t kPolyMask, bool kPair>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -173,7 +176,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(q_full, 1);
     for (int i = 0; i < kKvSlots; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], kPair ? 2 : 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
@@ -187,9 +190,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tmem_relinquish<1>();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync(); else __syncthreads();   // the peer's barriers must exist before anything lands on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t pair_rank = kPair ? cluster_ctarank() : 0u;
 
   if (warp_idx < 4) {
     reg_dec<56>();
@@ -208,8 +212,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const CUtensorMap* tm = (i & 1) ? &tmap_v : &tmap_k;
         uint8_t* dst = smem_kv + slot * kTileBytes;
         const int row = (i >> 1) * kTileKV;
-        tma_load_2d(dst, tm, &kv_full[slot], col, row);
-        tma_load_2d(dst + kBoxBytes, tm, &kv_full[slot], col + 64, row);
+        if constexpr (kPair) {     // my 64 rows of the tile, into both CTAs (box = 64 rows x 64 columns = 8 KB)
+          const int half = static_cast<int>(pair_rank) * (kTileKV / 2);
+          tma_load_2d_mcast(dst + half * 128, tm, &kv_full[slot], col, row + half, 0x3);
+          tma_load_2d_mcast(dst + kBoxBytes + half * 128, tm, &kv_full[slot], col + 64, row + half, 0x3);
+        } else {
+          tma_load_2d(dst, tm, &kv_full[slot], col, row);
+          tma_load_2d(dst + kBoxBytes, tm, &kv_full[slot], col + 64, row);
+        }
         if (++slot == kKvSlots) { slot = 0; phase ^= 1; }
       }
     } else if (warp_idx == 1) {
@@ -239,7 +249,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           umma_commit(&s_full[t]);
         }
       }
-      if (leader) umma_commit(&kv_empty[slot]);
+      if (leader) {
+        if constexpr (kPair) umma_commit_mcast(&kv_empty[slot], 0x3); else umma_commit(&kv_empty[slot]);
+      }
       __syncwarp();
       if (++slot == kKvSlots) { slot = 0; phase ^= 1; }
       PROF_DECL;
@@ -277,7 +289,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           }
           if (leader) {
-            if (t == 1) umma_commit(&kv_empty[v_slot]);
+            if (t == 1) {
+              if constexpr (kPair) umma_commit_mcast(&kv_empty[v_slot], 0x3); else umma_commit(&kv_empty[v_slot]);
+            }
             if (more) {
 #pragma unroll
               for (int k = 0; k < kHeadDim / 16; ++k)
@@ -285,7 +299,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                            idesc_qk, k != 0);
             }
             umma_commit(&s_full[t]);   // S_t(j+1) ready (and P_t V_j done); after the last tile: O_t final
-            if (more && t == 1) umma_commit(&kv_empty[k_slot]);
+            if (more && t == 1) {
+              if constexpr (kPair) umma_commit_mcast(&kv_empty[k_slot], 0x3); else umma_commit(&kv_empty[k_slot]);
+            }
           }
           __syncwarp();
         }
@@ -481,7 +497,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync(); else __syncthreads();   // no CTA leaves while its peer can still write into it
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
@@ -527,20 +543,45 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
   rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, kTileKV, 64);
   if (rc) return rc;
   // fraction of the exponentials computed on the FMA pipe; DRB_ATTN_POLY (0 -> 0/16, 1 -> 4/16, 2 -> 5/16, 3 -> 8/16,
-  // 4 -> 3/16, 5 -> 2/16, 6 -> 6/16, 7 -> 7/16) is a tuning switch only, the default is what was measured fastest on B200.
-  static int variant = -1;
+  // 4 -> 3/16, 5 -> 2/16, 6 -> 6/16, 7 -> 7/16) and DRB_ATTN_PAIR (0 = no K/V multicast) are tuning switches only, the
+  // defaults are what was measured fastest on B200.
+  static int variant = -1, pair_ok = 1;
   if (variant < 0) {
     const char* e = getenv("DRB_ATTN_POLY");
     variant = e ? atoi(e) : 2;
     if (variant < 0 || variant > 7) variant = 2;
-#define DRB_ATTN_CFG(mask) \
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<mask>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    DRB_ATTN_CFG(0x0000u) DRB_ATTN_CFG(0x1111u) DRB_ATTN_CFG(0x4924u) DRB_ATTN_CFG(0x5555u) DRB_ATTN_CFG(0x0421u) DRB_ATTN_CFG(0x0101u) DRB_ATTN_CFG(0x2929u) DRB_ATTN_CFG(0x52A5u)
+    e = getenv("DRB_ATTN_PAIR");
+    pair_ok = e ? atoi(e) : 1;
+#define DRB_ATTN_CFG(mask)                                                                                                        \
+    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<mask, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));       \
+    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<mask, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    DRB_ATTN_CFG(0x0000u) DRB_ATTN_CFG(0x1111u) DRB_ATTN_CFG(0x4924u) DRB_ATTN_CFG(0x5555u) DRB_ATTN_CFG(0x0421u) DRB_ATTN_CFG(0x0101u)
+    DRB_ATTN_CFG(0x2929u) DRB_ATTN_CFG(0x52A5u)
 #undef DRB_ATTN_CFG
   }
   dim3 grid((q_len + kTileQ * kQTilesPerCta - 1) / (kTileQ * kQTilesPerCta), num_heads);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define DRB_ATTN_LAUNCH(mask) attention_kernel<mask><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p);
+  const bool pair = pair_ok && (grid.x % 2 == 0);       // clusters of two adjacent query blocks of one head
+  if (pair) {   // K/V maps with 64-row boxes: each CTA of the pair loads (and multicasts) half of every tile
+    rc = make_tmap_2d_bf16(&tk, k, kv_len, cols, ld_qkv, kTileKV / 2, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, kTileKV / 2, 64);
+    if (rc) return rc;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = kAttnSmem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define DRB_ATTN_LAUNCH(mask)                                                                       \
+  if (pair) { DRB_CUDA(cudaLaunchKernelEx(&cfg, attention_kernel<mask, true>, tq, tk, tv, p)); }    \
+  else { DRB_CUDA(cudaLaunchKernelEx(&cfg, attention_kernel<mask, false>, tq, tk, tv, p)); }
   switch (variant) {
     case 0: DRB_ATTN_LAUNCH(0x0000u) break;
     case 1: DRB_ATTN_LAUNCH(0x1111u) break;
@@ -552,7 +593,6 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
     default: DRB_ATTN_LAUNCH(0x4924u) break;
   }
 #undef DRB_ATTN_LAUNCH
-  DRB_CUDA(cudaGetLastError());
   return 0;
 }
 
