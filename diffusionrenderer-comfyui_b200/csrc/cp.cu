@@ -3,9 +3,11 @@
 // Ulysses exchange (tokens-sharded <-> heads-sharded) is not a separate collective here: it is fused into the kernels on
 // either side of the attention,
 //
-//   drb_cp_qk_norm_rope_scatter  per-head RMSNorm + RoPE of the local tokens (CleanGeneralDIT.py:288-297, :45-84), with
-//                                each head's q / k / v row stored straight into the peer that owns the head
-//                                ([S, 3*D/P] buffer, P2P stores over NVLink) — the "all-to-all" is the kernel's output;
+//   drb_gemm_qkv_norm_rope       (gemm.cu) the QKV projection whose epilogue normalises / rotates q and k and stores each head's
+//                                q / k / v row straight into the peer that owns the head ([S, 3*D/P] buffer, P2P stores over
+//                                NVLink) — the "all-to-all" is the GEMM's output;
+//   drb_cp_qk_norm_rope_scatter  the same exchange as a stand-alone kernel after a plain QKV GEMM (CleanGeneralDIT.py:288-297,
+//                                :45-84); kept as the A/B reference of the fused form (74.9 vs 73.6 ms per step at P = 8);
 //   drb_attention_bf16_cp        (attention.cu) flash attention over the H/P local heads and all S tokens whose epilogue
 //                                stores each output row into the peer that owns the token;
 //   drb_cp_barrier               system-scope flag exchange between the P GPUs (one tiny kernel, no host involvement).

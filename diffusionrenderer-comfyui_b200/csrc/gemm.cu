@@ -7,7 +7,9 @@
 //   warp 0      TMA producer            (ring of kStages {A,B} k-blocks of 64)
 //   warp 1      tcgen05.mma issuer      (one thread; leader CTA only in pair mode)
 //   warp 2      TMEM allocator          (512 columns = 2 accumulator stages x 256 fp32 columns)
-//   warps 4..7  epilogue                (tcgen05.ld -> registers -> epilogue math -> 16-byte global stores)
+//   warps 4..7  epilogue                (tcgen05.ld -> registers -> epilogue math -> swizzled smem staging -> coalesced row stores)
+// Epilogues: store, exact-erf GELU, gated residual, and the QKV projection's (per-head RMSNorm + RoPE in registers, rows stored
+// locally or — under context parallelism — straight into the GPU that owns the head: drb_gemm_qkv_norm_rope).
 // kCtaGroup = 1: tile 128 x 256 per CTA.  kCtaGroup = 2: tile 256 x 256 per CTA pair (cta_group::2 MMA, each CTA
 // stages its own 128 rows of A and its own 128-row half of W, halving the shared-memory/L2 operand traffic).
 // The MMA of tile i+1 overlaps the epilogue of tile i through the two TMEM accumulator stages.
