@@ -211,10 +211,11 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
   const float rstd = bf16_round(rsqrtf(static_cast<float>(var_d) + 1e-6f));
   const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(t) * per_frame);
   uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(t) * per_frame);
-  const int64_t n8 = per_frame >> 3;
+  const int n8 = static_cast<int>(per_frame >> 3);     // per_frame < 2^34 is checked by the host
   const int c8 = C >> 3;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
-    const int cg = static_cast<int>(i % c8) * 8;
+#pragma unroll 2
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n8; i += gridDim.x * 256) {
+    const int cg = (i % c8) * 8;
     const uint4 v = src[i];
     const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma + cg));
     const uint4 b = __ldg(reinterpret_cast<const uint4*>(beta + cg));
@@ -224,9 +225,9 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
     for (int j = 0; j < 4; ++j) {
       float y0 = bf16_round((bf16_lo(vw[j]) - mean) * rstd * bf16_lo(gw[j]) + bf16_lo(bw[j]));
       float y1 = bf16_round((bf16_hi(vw[j]) - mean) * rstd * bf16_hi(gw[j]) + bf16_hi(bw[j]));
-      if (silu) {
-        y0 = y0 / (1.0f + __expf(-y0));
-        y1 = y1 / (1.0f + __expf(-y1));
+      if (silu) {   // x * sigmoid(x): exp and reciprocal are both MUFU ops (the kernel's floor); no full-precision division
+        y0 = __fdividef(y0, 1.0f + __expf(-y0));
+        y1 = __fdividef(y1, 1.0f + __expf(-y1));
       }
       o[j] = pack_bf16x2(y0, y1);
     }
@@ -460,6 +461,7 @@ extern "C" int drb_groupnorm_apply_cl(const void* x, void* out, const double* st
                                       int64_t hw, int C, int silu, void* stream) {
   DRB_REQUIRE(x && out && stats && gamma && beta, "null pointer");
   DRB_REQUIRE(T > 0 && T <= 65535 && hw > 0 && C > 0 && C % 8 == 0, "C must be a multiple of 8");
+  DRB_REQUIRE(hw * C < (1LL << 34), "frame too large");
   DRB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
                 reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "pointers must be 16-byte aligned");
   const int64_t per_frame = hw * C;
