@@ -236,8 +236,8 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
 }
 
 // ===================================================================== row softmax (in place, bf16 storage, fp32 math)
-// s[r, 0:cols] <- softmax(scale * s[r, 0:cols]); s[r, cols:ld] <- 0 (K padding of the P.V GEMM).  One block per row;
-// three passes over the row, which stays in L1/L2 (<= 64 KB).
+// s[r, 0:cols] <- softmax(scale * s[r, 0:cols]); s[r, cols:ld] <- 0 (K padding of the P.V GEMM).  One block per row:
+// rows of up to 16384 columns live in registers (one read, one write); longer rows take three passes through L1/L2.
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(__nv_bfloat16* __restrict__ s, int64_t ld, int cols, float scale_log2e) {
   __nv_bfloat16* row = s + static_cast<int64_t>(blockIdx.x) * ld;
@@ -258,6 +258,49 @@ softmax_rows_kernel(__nv_bfloat16* __restrict__ s, int64_t ld, int cols, float s
     __syncthreads();
     return bcast;
   };
+  if (n8 <= 256 * 8) {
+    // the whole row fits in registers (<= 16384 columns: 8 vectors per thread): one read, one write
+    uint4 v[8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n8) {
+        v[k] = row4[i];
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (i * 8 + 2 * j < cols) m = fmaxf(m, bf16_lo(w[j]));
+          if (i * 8 + 2 * j + 1 < cols) m = fmaxf(m, bf16_hi(w[j]));
+        }
+      }
+    }
+    m = block_reduce(m, true) * scale_log2e;
+    float e[8][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n8) {
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          e[k][2 * j] = (i * 8 + 2 * j < cols) ? exp2f(bf16_lo(w[j]) * scale_log2e - m) : 0.f;
+          e[k][2 * j + 1] = (i * 8 + 2 * j + 1 < cols) ? exp2f(bf16_hi(w[j]) * scale_log2e - m) : 0.f;
+          sum += e[k][2 * j] + e[k][2 * j + 1];
+        }
+      }
+    }
+    const float inv = 1.0f / block_reduce(sum, false);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n8)
+        row4[i] = make_uint4(pack_bf16x2(e[k][0] * inv, e[k][1] * inv), pack_bf16x2(e[k][2] * inv, e[k][3] * inv),
+                             pack_bf16x2(e[k][4] * inv, e[k][5] * inv), pack_bf16x2(e[k][6] * inv, e[k][7] * inv));
+    }
+    return;
+  }
   float m = -INFINITY;
   for (int i = threadIdx.x; i < n8; i += 256) {
     const uint4 v = row4[i];

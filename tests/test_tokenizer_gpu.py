@@ -176,6 +176,10 @@ def test_softmax_transpose_temporal_attention():
     ops.softmax_rows(s, cols, 0.3)
     assert (s[:, cols:] == 0).all()
     assert (s[:, :cols].float() - ref).abs().max() <= 2 ** -8
+    wide = (torch.randn(3, 17008, device=DEV, generator=gen(23)) * 3).bfloat16()          # > 16384 columns: the three-pass path
+    ref_w = torch.softmax(wide[:, :17001].float() * 0.2, dim=-1)
+    ops.softmax_rows(wide, 17001, 0.2)
+    assert (wide[:, 17001:] == 0).all() and (wide[:, :17001].float() - ref_w).abs().max() <= 2 ** -8 * ref_w.max()
     a = torch.randn(45, 3 * 64, device=DEV, generator=gen(19)).bfloat16()
     out = torch.full((64, 48), 7.0, device=DEV, dtype=torch.bfloat16)
     ops.transpose(a[:, 64:128], out)
