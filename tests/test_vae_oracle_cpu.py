@@ -84,3 +84,21 @@ def test_latent_frame_helpers():
     assert v.get_pixel_num_frames(8) == 57 and v.get_pixel_num_frames(16) == 121
     with pytest.raises(ValueError):
         v.encode(torch.zeros(3, 9, 8, 8))
+
+
+def test_unpinned_oracles_have_not_drifted():
+    """regression fixtures produced by the oracle itself (tests/golden/make_unpinned_regression.py): NOT upstream parity"""
+    import os
+
+    import numpy as np
+
+    from oracle import envmap_oracle as eo
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "unpinned_regression.npz"))
+    sd = vo.make_vae_state_dict(vo.SMALL_VAE, seed=7)
+    with torch.no_grad():
+        z = vo.encode(sd, vo.SMALL_VAE, torch.from_numpy(f["x"]))
+        y = vo.decode(sd, vo.SMALL_VAE, z)
+    assert np.allclose(z.numpy(), f["z"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(y[:, :, ::4, ::8, ::8].numpy(), f["y_sub"], rtol=1e-4, atol=1e-5)
+    env = eo.render_projection_from_panorama(torch.from_numpy(f["pano"]), (12, 20), 1.3, True, 180.0, cube_res=16)
+    assert np.allclose(env["env_ldr"].numpy(), f["env_ldr"], atol=1e-5) and np.allclose(env["env_log"].numpy(), f["env_log"], atol=1e-5)
