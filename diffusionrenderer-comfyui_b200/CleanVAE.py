@@ -465,6 +465,45 @@ class CleanVAE:
     def decode_scaled(self, latent_5d: torch.Tensor, scale: float) -> torch.Tensor:
         return self.model.decode_tensor(latent_5d, scale)
 
+    # Chunked form for clips longer than one tokenizer window — the behaviour of the upstream chunking tokenizer that the
+    # reference carries as (unused) `BasePretrainedVideoTokenizer.encode / .decode` (pretrained_vae.py:389-440): the clip is
+    # cut into windows of `pixel_chunk_duration` frames (121 for CV8x8x8: 16 latent frames each), every window is encoded
+    # / decoded on its own (so the first frame of every window is again the tokenizer's "image" frame) and the results
+    # are concatenated in time.
+    @staticmethod
+    def _latent_chunk(pixel_chunk_duration: int, factor: int = 8) -> int:
+        if (pixel_chunk_duration - 1) % factor:
+            raise ValueError(f"pixel_chunk_duration {pixel_chunk_duration} must be 1 + a multiple of {factor}")
+        return (pixel_chunk_duration - 1) // factor + 1
+
+    @torch.no_grad()
+    def encode_chunked(self, state_5d: torch.Tensor, pixel_chunk_duration: int = 121) -> torch.Tensor:
+        if state_5d.ndim != 5:
+            raise ValueError(f"CleanVAE expects a 5D input (B, C, T, H, W), but got {state_5d.shape}")
+        B, C, T, H, W = state_5d.shape
+        self._latent_chunk(pixel_chunk_duration, self.temporal_compression_factor)
+        if T % pixel_chunk_duration:
+            raise ValueError(f"Temporal dimension {T} is not divisible by chunk_length {pixel_chunk_duration}")
+        n = T // pixel_chunk_duration
+        chunks = state_5d.reshape(B, C, n, pixel_chunk_duration, H, W).permute(0, 2, 1, 3, 4, 5).reshape(B * n, C, pixel_chunk_duration, H, W)
+        z = self.encode(chunks)                                                   # (B*n, 16, t, h, w)
+        _, c, t, h, w = z.shape
+        return z.reshape(B, n, c, t, h, w).permute(0, 2, 1, 3, 4, 5).reshape(B, c, n * t, h, w)
+
+    @torch.no_grad()
+    def decode_chunked(self, latent_5d: torch.Tensor, pixel_chunk_duration: int = 121) -> torch.Tensor:
+        if latent_5d.ndim != 5:
+            raise ValueError(f"CleanVAE expects a 5D latent (B, C, T, H, W), but got {latent_5d.shape}")
+        B, c, T, h, w = latent_5d.shape
+        lc = self._latent_chunk(pixel_chunk_duration, self.temporal_compression_factor)
+        if T % lc:
+            raise ValueError(f"Temporal dimension {T} is not divisible by chunk_length {lc}")
+        n = T // lc
+        chunks = latent_5d.reshape(B, c, n, lc, h, w).permute(0, 2, 1, 3, 4, 5).reshape(B * n, c, lc, h, w)
+        y = self.decode(chunks)                                                   # (B*n, 3, pixel_chunk_duration, H, W)
+        _, C, t, H, W = y.shape
+        return y.reshape(B, n, C, t, H, W).permute(0, 2, 1, 3, 4, 5).reshape(B, C, n * t, H, W)
+
     def to(self, device):
         self.model = self.model.to(device)
         return self

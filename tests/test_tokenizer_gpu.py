@@ -258,3 +258,26 @@ def test_model_encode_decode_use_the_b200_tokenizer():
         vae.encode(x[0])
     with pytest.raises(ValueError):
         vae.decode(z[0])
+
+
+def test_chunked_encode_decode_equals_per_window_calls():
+    """encode_chunked / decode_chunked (the upstream chunking tokenizer's semantics, pretrained_vae.py:389-440): windows of
+    `pixel_chunk_duration` frames are tokenised independently and concatenated in time"""
+    vae, sd = _product_vae(vo.SMALL_VAE, seed=7)
+    pcd = 17                                             # 3 latent frames per window
+    x = (torch.rand(1, 3, 2 * pcd, 32, 48, device=DEV, generator=gen(31)) * 2 - 1).bfloat16()
+    z = vae.encode_chunked(x, pixel_chunk_duration=pcd)
+    assert z.shape == (1, 16, 6, 4, 6)
+    assert torch.equal(z[:, :, :3], vae.encode(x[:, :, :pcd])) and torch.equal(z[:, :, 3:], vae.encode(x[:, :, pcd:]))
+    sd16 = {k: v.bfloat16() for k, v in sd.items()}
+    ref = torch.cat([vo.encode(sd16, vo.SMALL_VAE, x[:, :, i * pcd:(i + 1) * pcd]) for i in range(2)], dim=2)
+    assert rel_l2(z, ref) <= 3e-2
+    y = vae.decode_chunked(z, pixel_chunk_duration=pcd)
+    assert y.shape == (1, 3, 2 * pcd, 32, 48)
+    assert torch.equal(y[:, :, pcd:], vae.decode(z[:, :, 3:]))
+    with pytest.raises(ValueError):
+        vae.encode_chunked(x[:, :, :30], pixel_chunk_duration=pcd)
+    with pytest.raises(ValueError):
+        vae.decode_chunked(z[:, :, :4], pixel_chunk_duration=pcd)
+    with pytest.raises(ValueError):
+        vae.encode_chunked(x, pixel_chunk_duration=16)
