@@ -158,3 +158,83 @@ def test_conv_argument_block_matches_the_header():
         _lib.call("drb_haar_patch", 8, 8, 3, 10, 32, 32, None)              # frames not 1 + 4k
     with pytest.raises(ValueError):
         _lib.call("drb_softmax_rows", 16, 12, 4, 12, 1.0, None)             # pitch not a multiple of 8
+
+
+# ------------------------------------------------------------------------------------------------ node surface (no ComfyUI)
+def test_node_registry_and_signatures_match_the_reference_surface():
+    """reference nodes.py:62-72, :131-149, :219-247, :313-323, :335-347"""
+    import inspect
+
+    import drb200
+    from drb200 import nodes
+    assert set(drb200.NODE_CLASS_MAPPINGS) == {"LoadDiffusionRendererModel", "Cosmos1InverseRenderer", "Cosmos1ForwardRenderer",
+                                               "LoadHDRImage"}
+    assert set(drb200.NODE_DISPLAY_NAME_MAPPINGS) == set(drb200.NODE_CLASS_MAPPINGS)
+    inv, fwd, load = nodes.Cosmos1InverseRenderer, nodes.Cosmos1ForwardRenderer, nodes.LoadDiffusionRendererModel
+    assert inv.RETURN_TYPES == ("IMAGE",) * 5 and inv.RETURN_NAMES == ("base_color", "metallic", "roughness", "normal", "depth")
+    assert inv.FUNCTION == "run_inverse_pass" and fwd.FUNCTION == "run_forward_pass" and load.FUNCTION == "load_pipeline"
+    assert inv.CATEGORY == fwd.CATEGORY == load.CATEGORY == "Cosmos1"
+    assert load.RETURN_TYPES == ("DIFFUSION_RENDERER_PIPELINE",) and fwd.RETURN_TYPES == ("IMAGE",)
+    assert list(inspect.signature(inv.run_inverse_pass).parameters) == ["self", "pipeline", "image", "guidance", "seed"]
+    assert list(inspect.signature(fwd.run_forward_pass).parameters) == [
+        "self", "pipeline", "depth", "normal", "roughness", "metallic", "base_color", "env_map", "guidance", "seed", "env_format",
+        "env_brightness", "env_flip_horizontal", "env_rotation"]
+    req = inv.INPUT_TYPES()
+    assert set(req["required"]) == {"pipeline", "image"} and set(req["optional"]) == {"guidance", "seed"}
+    assert set(fwd.INPUT_TYPES()["required"]) == {"pipeline", "depth", "normal", "roughness", "metallic", "base_color", "env_map"}
+    assert nodes.GBUFFER_INDEX_MAPPING == {"basecolor": 0, "metallic": 1, "roughness": 2, "normal": 3, "depth": 4}
+
+
+def test_image_inputs_are_normalised_like_the_reference():
+    """nodes.py:156-177: 3-D adds batch and time, 4-D adds time, lists are stacked, anything else raises"""
+    from drb200.nodes import _to_5d, latlong_vec
+    assert _to_5d(torch.zeros(8, 12, 3)).shape == (1, 1, 8, 12, 3)
+    assert _to_5d(torch.zeros(5, 8, 12, 3)).shape == (5, 1, 8, 12, 3)
+    assert _to_5d(torch.zeros(1, 9, 8, 12, 3)).shape == (1, 9, 8, 12, 3)
+    assert _to_5d([torch.zeros(9, 8, 12, 3)]).shape == (1, 9, 8, 12, 3)
+    with pytest.raises(ValueError):
+        _to_5d(torch.zeros(8, 12))
+    with pytest.raises(TypeError):
+        _to_5d("clip.mp4")
+    v = latlong_vec((6, 10))
+    assert v.shape == (6, 10, 3) and torch.allclose(v.norm(dim=-1), torch.ones(6, 10), atol=1e-6)
+
+
+def test_envmap_module_host_logic():
+    from drb200 import preprocess_envmap as pe
+    assert pe.process_comfyui_tensor(torch.zeros(2, 16, 32, 3)).shape == (16, 32, 3)
+    assert pe.process_comfyui_tensor(torch.zeros(1, 4, 16, 32)).shape == (16, 32, 3)      # (B,C,H,W) with alpha
+    assert pe.process_comfyui_tensor(torch.zeros(16, 32, 1)).shape == (16, 32, 3)
+    a, b = torch.rand(1, 8, 16, 3), torch.rand(1, 8, 16, 3)
+    assert pe.compute_tensor_hash(a) == pe.compute_tensor_hash(a.clone()) != pe.compute_tensor_hash(b)
+    assert pe._key(a, (4, 8), "proj", 1.0, True, 180.0) != pe._key(a, (4, 8), "proj", 1.5, True, 180.0)
+    cache = pe.EnvironmentMapCache(max_size=2)
+    for i in range(3):
+        cache.put(("k", i), {"env_ldr": i})
+    assert cache.get(("k", 0)) is None and cache.get(("k", 2)) == {"env_ldr": 2}
+    with pytest.raises(ValueError):
+        pe.render_projection_from_panorama(3.14, (8, 8))
+    with pytest.raises(ValueError):                                                     # CPU tensor: the device path refuses
+        pe.render_projection_from_panorama(torch.rand(8, 16, 3), (4, 8), device="cpu", use_cache=False)
+    with pytest.raises(RuntimeError):
+        pe.load_hdr_file("/nonexistent/file.hdr")
+
+
+def test_pipeline_surface_and_model_selection_errors():
+    """diffusion_renderer_pipeline.py:38-45, :99, :242"""
+    import inspect
+
+    from drb200.diffusion_renderer_pipeline import CleanDiffusionRendererPipeline as P
+    sig = inspect.signature(P.__init__).parameters
+    assert list(sig)[1:] == ["checkpoint_dir", "checkpoint_name", "model_type", "vae_instance", "model_instance", "guidance", "num_steps",
+                             "height", "width", "num_video_frames", "seed", "dtype"]
+    assert (sig["guidance"].default, sig["num_steps"].default, sig["seed"].default, sig["model_type"].default) == (2.0, 20, 42, "inverse")
+    p = P("", "", model_type="Inverse", model_instance=None)
+    assert p.model_type == "inverse"
+    p.config, p.model = {"x": 1}, object()
+    p.set_model_type("forward")
+    assert p.model_type == "forward" and p.config is None and p.model is None
+    with pytest.raises(ValueError):
+        p.generate_video({"context_index": torch.zeros(1, 1)})
+    with pytest.raises(RuntimeError):                      # no pre-loaded model: the reference's fallback is dead code (:227)
+        p.generate_video({"depth": torch.zeros(1, 3, 9, 64, 96)})
