@@ -1,29 +1,39 @@
 #!/usr/bin/env python
 """bench.py — DiT denoise steps/s of the 7B inverse renderer on a synthetic 57x704x1280 clip (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload inverse7b|tiny]
-                    [--parallel dp|cp] [--no-video] [--no-cpu-baseline]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload inverse7b|forward7b|tiny|tokenizer121]
+                    [--parallel auto|cp|dp|ring] [--cp-batch B] [--no-video] [--no-cpu-baseline] [--no-gpu-baseline]
 
 A "step" is ONE EDM Euler denoise step of one G-buffer pass: the sigma-only AdaLN vectors, c_in scaling + patchify,
-the 28-block GeneralDIT forward over S = 28 160 tokens and the unpatchify + Euler update (guidance 0, the node
-default).  N > 1 (torchrun, one rank per GPU): the five G-buffer passes / independent clips are data-parallel, every
-rank runs its own pass with replicated weights and no data-path collective, so scaling is "weak" and `value` is the
-whole-job steps/s = N*K / max-over-ranks time.  `--parallel cp` instead splits ONE video's token sequence over the N GPUs
-(context parallelism: Ulysses exchange fused into the kernels over NVLink peer memory, csrc/cp.cu): every rank works on
-the same step, `value` = K / max time, scaling "strong".
+the 28-block GeneralDIT forward over S = 28 160 tokens and the unpatchify + Euler update (guidance 0, the node default).
+
+N = 1: one pass per step on one GPU.
+N > 1 (torchrun, one rank per GPU), default `--parallel auto` = context parallelism: ONE video is split over the N GPUs —
+every rank owns 1/N of the token sequence, the Ulysses head exchange around self-attention is fused into the QKV GEMM /
+attention epilogues as P2P stores over NVLink (csrc/cp.cu) — and the five G-buffer passes of that video run batched along
+the token-row axis (B = 5 sequences per transformer pass).  One timed iteration is therefore 5 steps; `value` =
+5*K / max-over-ranks time, `ms_per_step` = iteration time / 5, scaling "strong" (the same video, N times the GPUs).  Before
+anything is timed every rank checks, on a small net, that the context-parallel forward and the batched sampler are
+bit-identical to the same model on one GPU (`cp_gate`).  The data-parallel alternative (rank r renders its own pass / clip,
+replicated weights, no collective, weak scaling) is timed afterwards in the same job and reported under `dp`.
 
 Keys beyond the base contract:
   roofline     the dominant kernel (flash attention, 53 % of the forward's FLOPs): algorithmic FLOPs per launch
-               (4*S*S*D) / its mean launch duration from CUDA events recorded inside the timed region, against the
-               measured sustained bf16 peak in MEASURED_PEAKS.json.
-  e2e          the same step through the public reference-facing call net.forward(x, timesteps, latent_condition,
-               context_index) with pinned HOST buffers: H2D of x / condition / sigma / context index and D2H of F inside
-               the timed region.
-  cpu_baseline the oracle (CPU restatement of the reference) timed on the host cores on a bounded sample.
+               (4*S*S*128 per head and sequence) / its mean launch duration from CUDA events recorded inside the timed
+               region, against the measured sustained bf16 peak in MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch
+               from the ncu --set full capture recorded in profiles/attention_traffic.json, valid only while the sha256
+               of csrc/attention.cu matches the one recorded there (else null + traffic_stale).
+  e2e          the same metric through the public API with pinned HOST buffers, H2D of the inputs and D2H of the result
+               inside the timed region: N = 1 net.forward(x, timesteps, latent_condition, context_index); N > 1
+               model.sample_latent(...) of one step for the five batched passes.
+  cpu_baseline the oracle (CPU restatement of the reference, pinned bit-exactly against it) timed on the host cores on a
+               bounded sample: one FA-CA-MLP block at the full S = 28 160, x28 by the exact FLOP ratio (`extrapolated`).
+  gpu_baseline the "existing Blackwell path": the reference's operator sequence through stock PyTorch (cuBLASLt, SDPA,
+               unfused elementwise) for one block on the same GPU, run back to back for >= 3 s, x28 (N = 1 only).
   step_tflops  whole-step achieved TFLOP/s (6.8132e14 algorithmic FLOP per step) and its fraction of the peak.
-  video        seconds per inverse-rendered video measured through the pipeline API (CleanDiffusionRendererPipeline
-               .generate_video x 5 G-buffer passes: H2D of the fp32 clip, tokenizer encode once, 15 Euler steps and one
-               decode + uint8 post-process + D2H per pass); with dp over N GPUs each rank renders ceil(5/N) passes.
+  host_enqueue_ms_per_step   host time to enqueue one step's launches (no CUDA graph: the host runs far ahead).
+  video        seconds per inverse-rendered video measured through the pipeline API (host fp32 clip in, host uint8
+               frames out): N = 1 generate_video x 5 passes; N > 1 generate_video_passes (one batched sampler run).
 `--impl reference` times the reference's own CPU implementation of the path (the oracle port, all host threads).
 """
 from __future__ import annotations
@@ -52,8 +62,11 @@ def emit(line: dict) -> None:
 
 WORKLOADS = {
     # name: (model_channels, blocks, heads, (frames, height, width))
-    "inverse7b": dict(D=4096, L=28, H=32, clip=(57, 704, 1280)),
-    "tiny": dict(D=512, L=4, H=4, clip=(9, 256, 256)),           # BASELINE configs[0] (parity / CPU-runnable case)
+    "inverse7b": dict(D=4096, L=28, H=32, clip=(57, 704, 1280), kind="inverse"),
+    # BASELINE configs[2]: the forward renderer — 8 conditions (5 G-buffers + 3 environment maps) -> 136 condition
+    # channels, K = 612 -> 616 patch GEMM, no context embedding (the cross-attention sub-block is the identity)
+    "forward7b": dict(D=4096, L=28, H=32, clip=(57, 704, 1280), kind="forward"),
+    "tiny": dict(D=512, L=4, H=4, clip=(9, 256, 256), kind="inverse"),   # BASELINE configs[0] (parity / CPU-runnable case)
     # BASELINE configs[4]: CV8x8x8 tokenizer encode + decode of a 121-frame 704x1280 clip per GPU (not the headline metric;
     # `python bench.py --workload tokenizer121` prints its own line: clips/s, TFLOP/s of the implicit-GEMM convolutions)
     "tokenizer121": dict(clip=(121, 704, 1280), enc_flop=3.566e13, dec_flop=6.128e13),
@@ -122,84 +135,131 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_sample(wl, n_timed: int, n_warm: int, tokens_div: int):
-    """One FA-CA-MLP block of the reference algorithm (oracle port, bf16, all host threads) on S/tokens_div tokens;
-    extrapolated to a full forward by the exact as-written FLOP ratio.  Returns (steps_per_s, info)."""
+def cpu_reference_sample(wl, n_timed: int, n_warm: int, budget_s: float = 150.0):
+    """One FA-CA-MLP block of the reference algorithm (oracle port — pinned bit-exactly against the imported reference,
+    tests/test_oracle_vs_reference.py — bf16, all host threads), scaled to a full forward by the exact as-written FLOP
+    ratio.  The block runs at the full S when (n_timed + n_warm) blocks fit `budget_s`, else on S/2 or S/4 tokens (whole
+    latent frames; attention is quadratic in S, so the ratio is computed for the sampled S).  Returns
+    (steps_per_s, info, seconds per timed sample)."""
     import torch
     from oracle import dit_oracle as do
     from oracle.weights import DitDims, make_state_dict
     D, H = wl["D"], wl["H"]
     c, t, h, w = latent_shape(wl["clip"])
     S = t * (h // 2) * (w // 2)
-    t_sub = max(1, t // tokens_div)
-    S_sub = t_sub * (h // 2) * (w // 2)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     dims = DitDims(model_channels=D, num_blocks=1, num_heads=H)
     sd = make_state_dict(dims, seed=0, dtype=torch.bfloat16)
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(S_sub, 1, D, generator=g).bfloat16()
     emb = torch.randn(1, D, generator=g).bfloat16()
     lora = (torch.randn(1, 3 * D, generator=g) * 0.1).bfloat16()
     ctx = torch.randn(1, 1, dims.crossattn_emb_channels, generator=g).bfloat16()
-    ang = do.rope_angles(dims, t_sub, h // 2, w // 2, torch.bfloat16, "cpu", sd["net.pos_embedder.seq"])
 
-    def one_block():
-        hcur = x
-        with torch.no_grad():
-            for j, kind in enumerate(("fa", "ca", "mlp")):
-                hcur = do.sub_block(sd, f"net.blocks.block0.blocks.{j}", kind, dims, hcur, emb, lora, ctx, ang)
-        return hcur
+    def make(t_sub):
+        S_sub = t_sub * (h // 2) * (w // 2)
+        x = torch.randn(S_sub, 1, D, generator=g).bfloat16()
+        ang = do.rope_angles(dims, t_sub, h // 2, w // 2, torch.bfloat16, "cpu", sd["net.pos_embedder.seq"])
 
+        def one_block():
+            hcur = x
+            with torch.no_grad():
+                for jj, kind in enumerate(("fa", "ca", "mlp")):
+                    hcur = do.sub_block(sd, f"net.blocks.block0.blocks.{jj}", kind, dims, hcur, emb, lora, ctx, ang)
+            return hcur
+        return S_sub, one_block
+
+    def block_flops(S_sub):
+        return flops_per_forward(D, 1, S_sub, as_written=True) - 2 * S_sub * D * (4 * 33 + 64)
+
+    # calibrate on a quarter of the frames, then take the largest sample that fits the budget
+    t_q = max(1, t // 4)
+    S_q, blk = make(t_q)
+    blk()
+    t0 = time.perf_counter()
+    blk()
+    t_cal = time.perf_counter() - t0
+    t_sub = t_q
+    for cand in (t, max(1, t // 2)):
+        S_c = cand * (h // 2) * (w // 2)
+        if t_cal * block_flops(S_c) / block_flops(S_q) * (n_timed + n_warm) <= budget_s:
+            t_sub = cand
+            break
+    if t_sub != t_q:
+        S_sub, blk = make(t_sub)
+    else:
+        S_sub = S_q
     for _ in range(n_warm):
-        one_block()
+        blk()
     times = []
     for _ in range(n_timed):
         t0 = time.perf_counter()
-        one_block()
+        blk()
         times.append(time.perf_counter() - t0)
     t_block = sum(times) / len(times)
-    f_block_sub = flops_per_forward(D, 1, S_sub, as_written=True) - 2 * S_sub * D * (4 * 33 + 64)
+    f_block_sub = block_flops(S_sub)
     f_forward = flops_per_forward(D, wl["L"], S, as_written=True)
     t_forward = t_block * f_forward / f_block_sub
-    info = {"kind": "port", "cores": cores,
+    info = {"kind": "port", "cores": cores, "extrapolated": True,
+            "port_pinned": "oracle port pinned bit-exactly (fp32, CPU) against the imported reference modules",
             "sample": f"1 FA-CA-MLP block (D={D}) of the oracle port in bf16 on {S_sub} of {S} tokens, {n_timed} timed runs of "
                       f"{t_block:.2f} s each, scaled to a {wl['L']}-block forward by the as-written FLOP ratio {f_forward / f_block_sub:.1f}",
+            "sample_tokens": S_sub, "full_tokens": S, "s_per_sample": t_block, "flop_ratio": f_forward / f_block_sub,
             "cpu_tflops": f_block_sub / t_block / 1e12}
-    return 1.0 / t_forward, info, sum(times)
+    return 1.0 / t_forward, info, t_block
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    div = 1 if args.workload == "tiny" else 4
-    value, info, total = cpu_reference_sample(wl, max(1, args.steps), max(1, args.warmup), div)
+    value, info, t_sample = cpu_reference_sample(wl, max(1, args.steps), max(1, args.warmup))
+    # `ms_per_step` is the measured wall time of one timed sample (so steps * ms_per_step is what this run really spent);
+    # `value` is the extrapolated whole-forward rate the sample implies, in the B200 arm's unit
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": config_block(args, wl),
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t_sample, "ms_per_full_step_extrapolated": 1000.0 / value,
+            "extrapolated": True, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config_block(args, wl, 1),
             "cpu_baseline": dict(info, value=value, unit=UNIT),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
 
-def config_block(args, wl):
+def cond_channels(wl):
+    return 16 if wl.get("kind", "inverse") == "inverse" else 136
+
+
+def config_block(args, wl, world, mode="single", batch=1):
     c, t, h, w = latent_shape(wl["clip"])
-    return {"workload": f"{args.workload}: GeneralDIT D={wl['D']} L={wl['L']} heads={wl['H']}, inverse renderer, "
-                        f"{wl['clip'][0]}x{wl['clip'][1]}x{wl['clip'][2]} clip -> latent 16x{t}x{h}x{w}, S={t * (h // 2) * (w // 2)} tokens, "
-                        "guidance 0, 15-step sigma schedule, random-init weights",
-            "parallelism": ("single GPU" if args.gpus <= 1 else
-                            f"cp{args.gpus}: one video's tokens split over the GPUs, Ulysses exchange fused into kernels over NVLink peer memory"
-                            if args.parallel == "cp" else
-                            f"ring{args.gpus}: one video's tokens split over the GPUs, K/V blocks pulled from peer memory in ring order"
-                            if args.parallel == "ring" else f"dp{args.gpus} over G-buffer passes (replicated weights, no collective)"),
+    kind = wl.get("kind", "inverse")
+    par = {"single": "single GPU",
+           "cp": f"cp{world}: one video's tokens split over the {world} GPUs (Ulysses head exchange fused into the QKV GEMM / attention "
+                 f"epilogues over NVLink peer memory), its {batch} G-buffer passes batched along the token-row axis",
+           "ring": f"ring{world}: one video's tokens split over the GPUs, K/V blocks pulled from peer memory in ring order",
+           "dp": f"dp{world}: {world} independent passes / clips, one per GPU (replicated weights, no collective)"}[mode]
+    return {"workload": f"{args.workload}: GeneralDIT D={wl['D']} L={wl['L']} heads={wl['H']}, {kind} renderer "
+                        f"({cond_channels(wl)} condition channels), {wl['clip'][0]}x{wl['clip'][1]}x{wl['clip'][2]} clip -> latent "
+                        f"16x{t}x{h}x{w}, S={t * (h // 2) * (w // 2)} tokens, guidance 0, 15-step sigma schedule, random-init weights",
+            "parallelism": par,
             "l2": "working set per kernel (>= 230 MB activations + 32..134 MB weights) exceeds the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-# DRAM traffic of one attention launch at S = 28 160, 32 heads, from the ncu --set full capture of this kernel
-# (profiles/r01_attention_final_ncu_raw.txt: dram__bytes_read.sum 704.1 MB + dram__bytes_write.sum 239.6 MB; algorithmic 923 MB)
-ATTN_NCU_TRAFFIC_BYTES = {(28160, 32): 943.6e6}
+def attention_traffic(S, heads):
+    """DRAM bytes per attention launch from the committed ncu --set full capture — only while csrc/attention.cu is the file
+    that was profiled (sha256 recorded next to the number)."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "attention_traffic.json")) as f:
+            rec = json.load(f)
+        with open(os.path.join(ROOT, "diffusionrenderer-comfyui_b200", "csrc", "attention.cu"), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+    except Exception as e:
+        return None, f"unavailable: {e}", None
+    val = rec.get("traffic_bytes", {}).get(f"{S}x{heads}")
+    if sha != rec.get("attention_cu_sha256"):
+        return None, rec.get("source"), True
+    return val, rec.get("source"), False
 
 
 def random_tokenizer(torch, dev):
@@ -217,42 +277,149 @@ def random_tokenizer(torch, dev):
     return vae
 
 
-def time_video(torch, dist, model, wl, rank, world, dev, cp_mode=False):
-    """One inverse-rendered video through the pipeline API: dp = the five G-buffer passes dealt over the ranks; cp = every
-    rank runs all five passes, each pass's token sequence split over the ranks (the tokenizer runs replicated).  Returns
-    (seconds max over ranks, passes of this rank, h2d bytes, d2h bytes)."""
+def cp_gate(torch, dist, cp, dev):
+    """Correctness gate of the multi-GPU path, run where the driver runs the bench: on a small net the context-parallel
+    forward, the context-parallel sampler and the sampler with batched passes + batched CFG must be BIT-IDENTICAL to the same
+    model on one GPU (every rank computes the one-GPU reference itself).  Returns a dict for the result line."""
+    from drb200 import diffusion_renderer_config as cfgm
+    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
+    cfg = cfgm.get_inverse_renderer_config(64, 96, 9)
+    cfg["model_type"] = "inverse"
+    cfg["net"].update(model_channels=1024, num_blocks=3, num_heads=8)
+    torch.manual_seed(0)
+    model = CleanDiffusionRendererModel(cfg).to(dev).to(torch.bfloat16)
+    model.net.init_weights_(seed=1)
+    T, H, W = 8, 16, 24                                   # 768 tokens; 96 per rank at P = 8
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(1, 16, T, H, W, device=dev, generator=g).bfloat16()
+    cond = (torch.randn(1, 16, T, H, W, device=dev, generator=g) * 0.5).bfloat16()
+    ci = torch.full((1, 1), 2, dtype=torch.long, device=dev)
+    sigma = torch.tensor(1.26, device=dev)
+    conds = [{"latent_condition": cond, "context_index": torch.full((1, 1), k, dtype=torch.long, device=dev)} for k in (0, 3, 4)]
+    unconds = [{"latent_condition": torch.zeros_like(cond), "context_index": torch.zeros_like(ci)} for _ in conds]
+    with torch.no_grad():
+        model.scheduler.set_timesteps(3, device=dev)
+        xt = x * model.scheduler.sigmas[0]
+        ref_f = model.net(x=x, timesteps=sigma, latent_condition=cond, context_index=ci)
+        ref_seq = torch.cat([model.sample_latent(xt, c, None) for c in conds])              # one pass at a time, one GPU
+        ref_cfg = torch.cat([model.sample_latent(xt, c, u, guidance=2.0) for c, u in zip(conds, unconds)])
+        model.net.enable_context_parallel(cp)
+        got_f = model.net(x=x, timesteps=sigma, latent_condition=cond, context_index=ci)
+        got_seq = model.sample_latent(xt, conds, None)                                       # batched passes, P GPUs
+        got_cfg = model.sample_latent(xt, conds, unconds, guidance=2.0)                      # batched passes x (cond, uncond)
+        model.net.enable_context_parallel(None)
+    torch.cuda.synchronize()
+    res = {"forward_identical": bool(torch.equal(got_f, ref_f)), "batched_sampler_identical": bool(torch.equal(got_seq, ref_seq)),
+           "batched_cfg_sampler_identical": bool(torch.equal(got_cfg, ref_cfg)), "finite": bool(torch.isfinite(got_cfg.float()).all())}
+    flag = torch.tensor([1 if all(res.values()) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["all_ranks_ok"] = bool(flag.item() == 1)
+    res["what"] = ("tiny GeneralDIT (D=1024, 3 blocks, 8 heads, 768 tokens): cp forward / 3-pass batched sampler / batched CFG sampler "
+                   "vs the same model on one GPU, torch.equal on every rank")
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def time_video(torch, dist, model, wl, rank, world, dev, mode):
+    """One inverse-rendered video through the pipeline API.  single: generate_video per pass (what the node's loop does);
+    dp: the five passes dealt over the ranks; cp: generate_video_passes — every rank calls it, the five passes run as one
+    batched sampler over the split token sequence, pass p is decoded by rank p mod P, frames land on rank 0.
+    Returns (seconds max over ranks, passes of this rank, h2d bytes, d2h bytes)."""
     from drb200.diffusion_renderer_pipeline import CleanDiffusionRendererPipeline
     f, hh, ww = wl["clip"]
     vae = random_tokenizer(torch, dev)
     pipe = CleanDiffusionRendererPipeline(checkpoint_dir="", checkpoint_name="", model_type="inverse", vae_instance=vae,
                                           model_instance=model, guidance=0.0, num_steps=15, seed=42)
     clip = (torch.rand(1, 3, f, hh, ww, generator=torch.Generator().manual_seed(1234)) * 2 - 1).pin_memory()   # host, fp32
-    mine = list(range(5)) if cp_mode else [p for p in range(5) if p % world == rank]
+    mine = list(range(5)) if mode in ("cp", "ring", "single") else [p for p in range(5) if p % world == rank]
 
     def render(passes, steps):
         pipe.num_steps = steps
-        out = None
+        if mode == "cp":
+            outs = pipe.generate_video_passes({"rgb": clip, "video": clip}, passes, normalize_normal=[p == 3 for p in passes], seed=42)
+            return [o for o in outs if o is not None]
+        outs = []
         with pipe.shared_conditions():
             for p in passes:
                 batch = {"rgb": clip, "video": clip, "context_index": torch.full((1, 1), p, dtype=torch.long)}
-                out = pipe.generate_video(batch, normalize_normal=(p == 3), seed=42)       # uint8 (1,T,H,W,3) on the host
-        return out
+                outs.append(pipe.generate_video(batch, normalize_normal=(p == 3), seed=42))   # uint8 (1,T,H,W,3) on the host
+        return outs
 
-    render(mine[:1] or [0], 1)                      # warm-up: allocations, tensor maps, tokenizer weight packing
+    render(mine if mode == "cp" else (mine[:1] or [0]), 1)   # warm-up: allocations, tensor maps, tokenizer weight packing
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out = render(mine, 15)
+    outs = render(mine, 15)
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     h2d = clip.numel() * 4 if mine else 0
-    d2h = (out.size if out is not None else 0) * len(mine)
+    d2h = sum(o.size for o in outs)
     pipe.vae_instance = None
     model.vae = None
     return dt.item(), len(mine), h2d, d2h
+
+
+def gpu_baseline(torch, min_seconds=3.0):
+    """stock-PyTorch block (tools/torch_gpu_baseline.py) back to back for >= min_seconds on this GPU"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("torch_gpu_baseline", os.path.join(ROOT, "tools", "torch_gpu_baseline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.measure(28160, min_seconds)
+
+
+def build_model(torch, wl, dev):
+    from drb200 import diffusion_renderer_config as cfgm
+    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
+    f, hh, ww = wl["clip"]
+    kind = wl.get("kind", "inverse")
+    cfg = cfgm.get_config_by_model_type(kind, hh, ww, f)
+    cfg["model_type"] = kind
+    cfg["net"].update(model_channels=wl["D"], num_blocks=wl["L"], num_heads=wl["H"])
+    with torch.device("meta"):
+        model = CleanDiffusionRendererModel(cfg)
+    model = model.to_empty(device=dev).to(torch.bfloat16)
+    model.net.init_weights_(seed=0)
+    return model
+
+
+def timed_steps(torch, dist, world, local, net, ws, xs, sig, use_ca, steps, warmup, timers):
+    """`warmup` untimed + `steps` timed denoise iterations on the latents `xs` ([N,16,T,H,W], restored every 15 steps);
+    returns (device ms of the timed region, host enqueue ms, launches, clock summary)."""
+    from drb200 import _lib
+    x_start = xs.clone()
+
+    def step(i, tm=None):
+        k = i % 15
+        if k == 0:
+            xs.copy_(x_start)
+        net.denoise_step(ws, xs, sig[k:k + 1], sig[k + 1:k + 2], use_ca, tm)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    launches0 = _lib.LAUNCHES
+    with ClockSampler(local) as clk:
+        e0.record()
+        h0 = time.perf_counter()
+        for i in range(steps):
+            step(warmup + i, timers)
+        host_ms = (time.perf_counter() - h0) * 1e3
+        e1.record()
+        sync()
+    if not torch.isfinite(xs.float()).all():
+        raise SystemExit("non-finite latent after the timed steps")
+    return e0.elapsed_time(e1), host_ms, _lib.LAUNCHES - launches0, clk.summary()
 
 
 def run_b200(args, wl):
@@ -265,91 +432,103 @@ def run_b200(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from drb200 import _lib
-    from drb200 import diffusion_renderer_config as cfgm
-    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
-
-    cp_mode = args.parallel in ("cp", "ring") and world > 1
-    f, hh, ww = wl["clip"]
-    cfg = cfgm.get_inverse_renderer_config(hh, ww, f)
-    cfg["model_type"] = "inverse"
-    cfg["net"].update(model_channels=wl["D"], num_blocks=wl["L"], num_heads=wl["H"])
-    with torch.device("meta"):
-        model = CleanDiffusionRendererModel(cfg)
-    model = model.to_empty(device=dev).to(torch.bfloat16)
-    net = model.net.init_weights_(seed=0)
     c, t, h, w = latent_shape(wl["clip"])
     S = t * (h // 2) * (w // 2)
-    # dp: rank r renders its own G-buffer pass of its own clip; cp: every rank holds the same clip and pass
-    g = torch.Generator(device=dev).manual_seed(1234 + (0 if cp_mode else rank))
-    cond = (torch.randn(1, 16, t, h, w, device=dev, generator=g) * 0.5).bfloat16()
-    ctx_idx = torch.full((1, 1), 0 if cp_mode else rank % 5, dtype=torch.long, device=dev)
+    mode = args.parallel
+    if mode == "auto":
+        mode = "single" if world == 1 else ("cp" if wl["H"] % world == 0 and t % world == 0 else "dp")
+    if world == 1:
+        mode = "single"
+    batch = args.cp_batch if mode == "cp" else 1
+
+    cp, gate = None, None
+    if mode in ("cp", "ring"):
+        from drb200.context_parallel import ContextParallel, shard_frames
+        cp = ContextParallel(mode="ring" if mode == "ring" else "ulysses")
+        if mode == "cp":
+            gate = cp_gate(torch, dist, cp, dev)
+            if not gate["all_ranks_ok"]:
+                if rank == 0:
+                    emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "error": "cp_gate failed", "cp_gate": gate})
+                raise SystemExit("context-parallel correctness gate failed")
+
+    model = build_model(torch, wl, dev)
+    net = model.net
+    cc = cond_channels(wl)
+    # cp: every rank holds the same clip and the same five passes; single / dp: rank r renders its own pass of its own clip
+    g = torch.Generator(device=dev).manual_seed(1234 + (0 if cp is not None else rank))
+    cond = (torch.randn(1, cc, t, h, w, device=dev, generator=g) * 0.5).bfloat16()
     model.scheduler.set_timesteps(15, device=dev)
     sig = model.scheduler.sigmas.contiguous()
     x0 = (torch.randn(1, 16, t, h, w, device=dev, generator=g).bfloat16() * sig[0]).bfloat16()
+    inverse = wl.get("kind", "inverse") == "inverse"
 
-    cp = None
-    t0f, t1f = 0, t
-    if cp_mode:
-        from drb200.context_parallel import ContextParallel, shard_frames
-        cp = ContextParallel(mode="ring" if args.parallel == "ring" else "ulysses")
-        net.enable_context_parallel(cp)
-        t0f, t1f = shard_frames(t, rank, world)
-    tl = t1f - t0f
-    net._ensure_packed()
-    ws = net._workspace(tl, h, w, dev, cp)
-    net.prepare_condition(ws, cond[:, :, t0f:t1f], tl, h, w)
-    use_ca = net.prepare_context(ws, net.context_token(ctx_idx))
-    x_start = x0[0][:, t0f:t1f].contiguous()
-    x = x_start.clone()
+    def setup(cp_obj, nseq, first_pass):
+        """workspace + constants of `nseq` passes (context indices first_pass, first_pass+1, ...) for this rank's frames"""
+        t0f, t1f = (0, t) if cp_obj is None else shard_frames(t, rank, world)
+        tl = t1f - t0f
+        net.enable_context_parallel(cp_obj)
+        net._ensure_packed()
+        ws = net._workspace(tl, h, w, dev, cp_obj, batch=nseq)
+        use_ca = False
+        for b in range(nseq):
+            net.prepare_condition(ws, cond[:, :, t0f:t1f], tl, h, w, b)
+            ctx = net.context_token(torch.full((1, 1), (first_pass + b) % 5, dtype=torch.long, device=dev)) if inverse else None
+            use_ca = net.prepare_context(ws, ctx, b)
+        xs = x0[:, :, t0f:t1f].expand(nseq, -1, -1, -1, -1).contiguous().clone()
+        return ws, xs, use_ca
 
-    def step(i, timers=None):
-        k = i % 15
-        if k == 0:
-            x.copy_(x_start)
-        net.denoise_step(ws, x, sig[k:k + 1], sig[k + 1:k + 2], use_ca, timers)
+    ws, xs, use_ca = setup(cp, batch, 0 if cp is not None else rank)
+    timers = []
+    ms, host_ms, launches, clocks = timed_steps(torch, dist, world, local, net, ws, xs, sig, use_ca, args.steps, args.warmup, timers)
+    attn_ms = statistics.mean(a.elapsed_time(b) for a, b in timers)
+
+    # ---- e2e: the public call with pinned host buffers (H2D + D2H inside the timed region)
+    hx = x0.cpu().pin_memory()
+    hcond = cond.cpu().pin_memory()
+    hsig = sig[:15].cpu().pin_memory()
+    n_e2e = max(2, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    timers = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    launches0 = _lib.LAUNCHES
-    with ClockSampler(local) as clk:
-        e0.record()
-        for i in range(args.steps):
-            step(args.warmup + i, timers)
-        e1.record()
-        sync()
-    launches = _lib.LAUNCHES - launches0
-    ms = e0.elapsed_time(e1)
-    attn_ms = statistics.mean(a.elapsed_time(b) for a, b in timers)
-    if not torch.isfinite(x.float()).all():
-        raise SystemExit("non-finite latent after the timed steps")
+    if mode == "cp":
+        # one public sampler call per timed iteration: model.sample_latent over the `batch` passes for ONE Euler step
+        hidx = [torch.full((1, 1), b % 5, dtype=torch.long).pin_memory() for b in range(batch)]
+        hout = torch.empty((batch, 16, t, h, w), dtype=torch.bfloat16).pin_memory()
+        e2e_api = ("CleanDiffusionRendererModel.sample_latent(xt, [5 condition dicts]) for one Euler step per call, pinned host "
+                   "tensors in (latent, latent condition, context indices, sigma pair), 5 host latents out")
+        units_per_call = batch
 
-    # ---- e2e: the public net.forward call with pinned host buffers (H2D + D2H inside the timed region); under cp every
-    # rank passes the same full tensors and receives the full F (frame slices are exchanged by the final all-gather)
-    hx = x0.cpu().pin_memory()
-    hcond = cond.cpu().pin_memory()
-    hidx = ctx_idx.cpu().pin_memory()
-    hsig = sig[:15].cpu().pin_memory()
-    hout = torch.empty((1, 16, t, h, w), dtype=torch.bfloat16).pin_memory()
+        def e2e_step(i):
+            k = i % 14
+            model.scheduler.sigmas = hsig[k:k + 2].to(dev, non_blocking=True)
+            dx = hx.to(dev, non_blocking=True)
+            dc = hcond.to(dev, non_blocking=True)
+            conds = [{"latent_condition": dc, "context_index": hi.to(dev, non_blocking=True)} for hi in hidx]
+            hout.copy_(model.sample_latent(dx, conds, None), non_blocking=True)
+        h2d = hx.numel() * 2 + hcond.numel() * 2 + batch * 8 + 8
+        d2h = hout.numel() * 2
+    else:
+        hidx = torch.full((1, 1), rank % 5, dtype=torch.long).pin_memory()
+        hout = torch.empty((1, 16, t, h, w), dtype=torch.bfloat16).pin_memory()
+        e2e_api = "CleanDiffusionRendererGeneralDIT.forward(x, timesteps, latent_condition, context_index) with pinned host tensors"
+        units_per_call = 1
 
-    def e2e_step(i):
-        k = i % 15
-        dx = hx.to(dev, non_blocking=True)
-        dc = hcond.to(dev, non_blocking=True)
-        di = hidx.to(dev, non_blocking=True)
-        ds = hsig[k:k + 1].to(dev, non_blocking=True)
-        out = net(x=model.scheduler.scale_model_input(dx, ds), timesteps=ds, latent_condition=dc, context_index=di)
-        hout.copy_(out, non_blocking=True)
+        def e2e_step(i):
+            k = i % 15
+            dx = hx.to(dev, non_blocking=True)
+            dc = hcond.to(dev, non_blocking=True)
+            di = hidx.to(dev, non_blocking=True)
+            ds = hsig[k:k + 1].to(dev, non_blocking=True)
+            out = net(x=model.scheduler.scale_model_input(dx, ds), timesteps=ds, latent_condition=dc, context_index=di)
+            hout.copy_(out, non_blocking=True)
+        h2d = hx.numel() * 2 + hcond.numel() * 2 + hidx.numel() * 8 + 4
+        d2h = hout.numel() * 2
 
-    n_e2e = max(2, min(args.steps, 5))
     e2e_step(0)
     sync()
     e0.record()
@@ -358,63 +537,98 @@ def run_b200(args, wl):
     e1.record()
     sync()
     e2e_ms = e0.elapsed_time(e1)
-    h2d = hx.numel() * 2 + hcond.numel() * 2 + hidx.numel() * 8 + 4
-    d2h = hout.numel() * 2
+    model.scheduler.set_timesteps(15, device=dev)
 
     video = None
-    if not args.no_video:
-        v_s, v_passes, v_h2d, v_d2h = time_video(torch, dist, model, wl, rank, world, dev, cp_mode)
-        video = {"s_per_video": v_s, "passes_per_rank": 5 if cp_mode else -(-5 // world), "passes_rank0": v_passes, "steps_per_pass": 15,
-                 "h2d_bytes_rank0": v_h2d, "d2h_bytes_rank0": v_d2h,
-                 "api": "CleanDiffusionRendererPipeline.generate_video per G-buffer pass (host fp32 clip in, host uint8 frames out), "
-                        "tokenizer encode once + 15 Euler steps + decode + post-process per pass; random-init tokenizer"}
+    if not args.no_video and inverse:
+        v_s, v_passes, v_h2d, v_d2h = time_video(torch, dist, model, wl, rank, world, dev, mode)
+        video = {"s_per_video": v_s, "passes_rank0": v_passes, "steps_per_pass": 15, "h2d_bytes_rank0": v_h2d, "d2h_bytes_rank0": v_d2h,
+                 "api": ("CleanDiffusionRendererPipeline.generate_video_passes: host fp32 clip in, tokenizer encode, ONE 15-step sampler run "
+                         "over the 5 batched passes, decode + post-process of pass p on rank p mod N, host uint8 frames out on rank 0"
+                         if mode == "cp" else
+                         "CleanDiffusionRendererPipeline.generate_video per G-buffer pass (host fp32 clip in, host uint8 frames out), "
+                         "tokenizer encode once + 15 Euler steps + decode + post-process per pass") + "; random-init tokenizer"}
 
-    t_loc = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    # ---- the data-parallel alternative, timed in the same job (N > 1 only): one independent pass per GPU
+    dp = None
+    if mode == "cp" and not args.no_dp_leg:
+        ws_dp, xs_dp, use_ca_dp = setup(None, 1, rank)
+        k_dp = max(2, min(args.steps, 4))
+        ms_dp, _, _, _ = timed_steps(torch, dist, world, local, net, ws_dp, xs_dp, sig, use_ca_dp, k_dp, 3, None)
+        t_dp = torch.tensor([ms_dp], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_dp, op=dist.ReduceOp.MAX)
+        dp_sps = world * k_dp / (t_dp.item() / 1e3)
+        dp = {"value": dp_sps, "unit": UNIT, "scaling": "weak", "steps": k_dp, "ms_per_step": t_dp.item() / k_dp,
+              "parallelism": f"dp{world}: {world} independent passes / clips, one per GPU (replicated weights, no collective)",
+              "s_per_video_dit_only": -(-5 // world) * 15 * (t_dp.item() / k_dp) / 1e3}
+
+    t_loc = torch.tensor([ms, e2e_ms, host_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_loc, op=dist.ReduceOp.MAX)
-    ms_max, e2e_max = t_loc.tolist()
+    ms_max, e2e_max, host_max = t_loc.tolist()
     if rank == 0:
         pk = peaks()
-        units = 1 if cp_mode else world                       # videos-in-flight: cp works on one step together
+        # single: one pass per iteration; cp: `batch` passes of one video per iteration (all ranks together); dp / ring-unbatched:
+        # one pass per rank (dp) or one pass for all (ring)
+        units = {"single": 1, "cp": batch, "ring": 1, "dp": world}[mode]
         steps_per_s = units * args.steps / (ms_max / 1e3)
-        F = flops_per_forward(wl["D"], wl["L"], S)
-        heads_local = wl["H"] // world if cp_mode else wl["H"]
-        # per layer and rank: ulysses = all S x S for H/P heads (one launch); ring = S/P rows x S keys for all heads (P launches,
-        # timed together) — the same FLOPs
-        attn_flops = 4.0 * S * S * 128 * heads_local
+        F = flops_per_forward(wl["D"], wl["L"], S, c_in=17 + cc)
+        seqs_heads = batch * wl["H"] // world if mode == "cp" else wl["H"]
+        # per attention stage and rank: cp = S x S for batch*H/P (sequence, head) pairs in one launch; single / dp = S x S for
+        # H heads; ring = the same FLOPs as P block launches timed together
+        attn_flops = 4.0 * S * S * 128 * (seqs_heads if mode != "ring" else wl["H"] // world)
         peak = pk["bf16_tflops_sustained"]
         ach = attn_flops / (attn_ms / 1e3) / 1e12
-        step_tf = F * steps_per_s / 1e12 / world              # per-GPU achieved TFLOP/s
+        gpus_sharing = world if mode in ("cp", "ring", "dp") else 1
+        step_tf = F * steps_per_s / 1e12 / gpus_sharing        # per-GPU achieved TFLOP/s
+        traffic, traffic_src, stale = attention_traffic(S, seqs_heads)
         line = {
             "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if cp_mode else "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_block(args, wl),
-            "e2e": {"value": units * n_e2e / (e2e_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "CleanDiffusionRendererGeneralDIT.forward(x, timesteps, latent_condition, context_index) with pinned host tensors"},
+            "ms_per_step": ms_max / args.steps / (batch if mode == "cp" else 1), "higher_is_better": True,
+            "scaling": "strong" if mode in ("cp", "ring") else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_block(args, wl, world, mode, batch),
+            "e2e": {"value": (units if mode != "cp" else units_per_call) * n_e2e / (e2e_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "api": e2e_api},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "attention_kernel (drb_attention_bf16)", "achieved": ach, "peak": peak,
-                         "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": ATTN_NCU_TRAFFIC_BYTES.get((S, heads_local)),
-                         "traffic_source": "profiles/r01_attention_final_ncu_raw.txt (ncu --set full, dram read + write per launch, bytes)",
+            "roofline": {"bound": "tensor", "kernel": "attention_kernel (drb_attention_bf16*)", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": pk["source"] + " sustained bf16",
                          "launch_ms": attn_ms, "launches_timed": len(timers), "flops_per_launch": attn_flops,
                          "share_of_step": attn_ms * wl["L"] / (ms / args.steps)},
             "step_tflops": {"achieved_per_gpu": step_tf, "flops_per_step": F, "frac_of_sustained_peak": step_tf / peak,
                             "frac_of_burst_peak": step_tf / pk["bf16_tflops"]},
+            "host_enqueue_ms_per_step": host_max / args.steps / (batch if mode == "cp" else 1),
             # one inverse video = 5 G-buffer passes x 15 steps (DiT only; the measured end-to-end figure is `video`)
-            "s_per_video_dit_only": 5 * 15 / steps_per_s if cp_mode else -(-5 // world) * 15 / (steps_per_s / world),
-            "clocks": clk.summary(),
+            "s_per_video_dit_only": 5 * 15 / steps_per_s if mode != "dp" else -(-5 // world) * 15 / (steps_per_s / world),
+            "clocks": clocks,
         }
+        if stale:
+            line["roofline"]["traffic_stale"] = "csrc/attention.cu changed since the ncu capture recorded in profiles/attention_traffic.json"
+        if mode == "cp":
+            line["ms_per_iteration"] = ms_max / args.steps
+            line["passes_per_iteration"] = batch
+            line["cp_gate"] = gate
+        if dp is not None:
+            line["dp"] = dp
         if video is not None:
             line["video"] = video
+        if world == 1 and not args.no_gpu_baseline and args.workload == "inverse7b":
+            try:
+                del ws, xs
+                net._ws.clear()
+                torch.cuda.empty_cache()
+                line["gpu_baseline"] = gpu_baseline(torch)
+            except Exception as e:
+                line["gpu_baseline"] = {"value": None, "unit": UNIT, "error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                v, info, _ = cpu_reference_sample(wl, 2, 1, 1 if args.workload == "tiny" else 4)
+                v, info, _ = cpu_reference_sample(wl, 2, 1, budget_s=60.0)
                 line["cpu_baseline"] = dict(info, value=v, unit=UNIT)
             except Exception as e:   # the GPU number stands on its own; say why the CPU leg is missing
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         emit(line)
     if cp is not None:
+        net.enable_context_parallel(None)
         cp.close()
     if world > 1:
         dist.destroy_process_group()
@@ -486,9 +700,13 @@ def main():
     ap.add_argument("--workload", default="inverse7b", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true", help="skip the measured end-to-end video leg")
-    ap.add_argument("--parallel", default="dp", choices=["dp", "cp", "ring"],
-                    help="N > 1: dp = one G-buffer pass per GPU (weak scaling, default); cp = one video split over the GPUs with "
-                         "the Ulysses head exchange fused into the kernels; ring = the same split with the ring K/V schedule")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch block on the same GPU (N = 1)")
+    ap.add_argument("--no-dp-leg", action="store_true", help="N > 1: skip the extra data-parallel measurement")
+    ap.add_argument("--cp-batch", type=int, default=5, help="G-buffer passes batched per context-parallel iteration")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "dp", "cp", "ring"],
+                    help="N > 1: auto = cp when N divides the heads and the latent frames; cp = one video split over the GPUs "
+                         "(Ulysses exchange fused into the kernels, passes batched); dp = one independent pass per GPU (weak "
+                         "scaling); ring = the cp split with the ring K/V schedule")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.workload.startswith("tokenizer"):

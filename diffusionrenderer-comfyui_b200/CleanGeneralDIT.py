@@ -251,30 +251,35 @@ class CleanGeneralDIT(nn.Module):
         self._cp = cp
         self._ws.clear()
 
-    def _workspace(self, T: int, H: int, W: int, dev, cp=None) -> Dict[str, torch.Tensor]:
-        """Activation buffers for one clip shape (allocated once, reused every forward).  With `cp`, T counts the latent
-        frames of THIS rank: token buffers hold the local S/P tokens, `a2a` [S, 3D/P] receives this rank's heads of every
-        token, and `attn` / `a2a` are peer-mapped so that the other ranks' kernels store into them directly."""
-        key = (T, H, W, dev, id(cp))
+    def _workspace(self, T: int, H: int, W: int, dev, cp=None, batch: int = 1) -> Dict[str, torch.Tensor]:
+        """Activation buffers for one clip shape (allocated once, reused every forward).  `batch` independent token
+        sequences (the five G-buffer passes of a clip, cond + uncond under CFG) are stacked along the row axis: every
+        token buffer holds batch * S rows, sequence b in rows [b*S, (b+1)*S).  With `cp`, T counts the latent frames of
+        THIS rank: S is the local token count, `a2a` [S*P, 3*batch*D/P] receives this rank's heads of every token of
+        every sequence, and `attn` / `a2a` are peer-mapped so that the other ranks' kernels store into them directly."""
+        key = (T, H, W, dev, id(cp), batch)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
         D, L = self.model_channels, self.num_blocks
         S = T * (H // 2) * (W // 2)
+        R = batch * S
         new = lambda *s, dtype=BF16: torch.empty(*s, device=dev, dtype=dtype)
         kpad = self._packed["wx"].shape[1]
         world, rank = (cp.world, cp.rank) if cp is not None else (1, 0)
+        if batch > 1 and cp is not None and (cp.mode == "ring" or S < 32):
+            raise ValueError("batched sequences under context parallelism need the Ulysses mode and >= 32 local tokens")
         cos, sin = self.pos_embedder.tables(T * world, H // 2, W // 2, BF16)
-        cos, sin = cos[rank * S:(rank + 1) * S].contiguous(), sin[rank * S:(rank + 1) * S].contiguous()
+        cos, sin = cos[rank * S:(rank + 1) * S].repeat(batch, 1).contiguous(), sin[rank * S:(rank + 1) * S].repeat(batch, 1).contiguous()
         ws = {
-            "S": S, "tok": torch.zeros(S, kpad, device=dev, dtype=BF16), "x": new(S, D), "xm": new(S, D),
-            "h": new(S, self.hidden), "y": new(S, self.out_patch_dim), "cos": cos, "sin": sin,
+            "S": S, "B": batch, "tok": torch.zeros(R, kpad, device=dev, dtype=BF16), "x": new(R, D), "xm": new(R, D),
+            "h": new(R, self.hidden), "y": new(R, self.out_patch_dim), "cos": cos, "sin": sin,
             "e": new(D), "emb": new(D), "t1": new(D), "lora": new(3 * D), "mod_h": new(3 * L + 1, self.adaln_lora_dim),
-            "mod": new(3 * L + 1, 3 * D), "ca_tmp": new(L, D), "ca_vec": new(L, D), "sigma": new(1, dtype=torch.float32),
-            "cp": cp,
+            "mod": new(3 * L + 1, 3 * D), "ca_tmp": new(batch, L, D), "ca_vec": new(batch, L, D),
+            "sigma": new(1, dtype=torch.float32), "qk_bound": new(L, dtype=torch.float32), "cp": cp,
         }
         if cp is None:
-            ws["attn"], ws["qkv"] = new(S, D), new(S, 3 * D)
+            ws["attn"], ws["qkv"] = new(R, D), new(R, 3 * D)
         elif cp.mode == "ring":
             # every rank's [q | k | v] rows are visible to the others; remote K/V blocks land in two staging buffers of the
             # same row pitch (only their k | v columns are written); fp32 running softmax state of the local query rows
@@ -284,14 +289,14 @@ class CleanGeneralDIT(nn.Module):
             ws["ring_o"] = new(S, D, dtype=torch.float32)
             ws["ring_ml"] = new(S, self.num_heads, 2, dtype=torch.float32)
         else:
-            ws["attn"], ws["attn_ptrs"] = cp.alloc("attn", (S, D))
-            ws["a2a"], ws["a2a_ptrs"] = cp.alloc("a2a", (S * world, 3 * D // world))
+            ws["attn"], ws["attn_ptrs"] = cp.alloc("attn", (R, D))
+            ws["a2a"], ws["a2a_ptrs"] = cp.alloc("a2a", (S * world, 3 * batch * D // world))
         self._ws = {key: ws}   # one live shape at a time: the buffers are large (MLP hidden = 0.92 GB at 57x704x1280)
         return ws
 
     # ------------------------------------------------------------------------------------------------ stages
-    def prepare_condition(self, ws, latent_condition: Optional[torch.Tensor], T: int, H: int, W: int) -> None:
-        """Constant token features of a pass: condition channels, ones padding mask, zero K-padding (:669-675)."""
+    def prepare_condition(self, ws, latent_condition: Optional[torch.Tensor], T: int, H: int, W: int, b: int = 0) -> None:
+        """Constant token features of sequence `b`: condition channels, ones padding mask, zero K-padding (:669-675)."""
         c0 = self.in_channels
         ones = c0 + self.additional_concat_ch if self.concat_padding_mask else -1
         cond = None
@@ -300,26 +305,35 @@ class CleanGeneralDIT(nn.Module):
             if cond.shape[0] != self.additional_concat_ch:
                 raise ValueError(f"latent_condition has {cond.shape[0]} channels, the net expects {self.additional_concat_ch}")
             cond = cond.to(BF16).contiguous()
-        ops.patchify_condition(cond, ws["tok"], c0, T, H, W, ones_channel=ones, zero_from=self.patch_dim)
+        ops.patchify_condition(cond, self._rows(ws, "tok", b), c0, T, H, W, ones_channel=ones, zero_from=self.patch_dim)
 
-    def prepare_context(self, ws, ctx: Optional[torch.Tensor]) -> bool:
-        """ca_vec[i] = to_out_i(to_v_i(ctx)) for every block (reference :268-306 with one key: softmax == 1).
+    @staticmethod
+    def _rows(ws, name: str, b: int) -> torch.Tensor:
+        """rows of sequence b in a token buffer"""
+        S = ws["S"]
+        return ws[name][b * S:(b + 1) * S]
+
+    def prepare_context(self, ws, ctx: Optional[torch.Tensor], b: int = 0) -> bool:
+        """ca_vec[b, i] = to_out_i(to_v_i(ctx)) for every block (reference :268-306 with one key: softmax == 1).
         Returns False when the context is all zeros (forward renderer): the sub-block is then the identity."""
         if ctx is None:
             return False
         P = self._packed
-        ops.gemv_batched(P["ca_v"], ctx.reshape(-1).contiguous(), ws["ca_tmp"])
-        ops.gemv_batched(P["ca_o"], ws["ca_tmp"], ws["ca_vec"])
+        ops.gemv_batched(P["ca_v"], ctx.reshape(-1).contiguous(), ws["ca_tmp"][b])
+        ops.gemv_batched(P["ca_o"], ws["ca_tmp"][b], ws["ca_vec"][b])
         return True
 
     def modulation(self, ws, sigma_dev: torch.Tensor) -> None:
-        """Everything that depends only on sigma: embedding, AdaLN-LoRA vector, all 3L+1 (shift, scale, gate) rows."""
+        """Everything that depends only on sigma: embedding, AdaLN-LoRA vector, all 3L+1 (shift, scale, gate) rows —
+        shared by every sequence of the batch — and the per-layer certificate of the max-free softmax (from the q/k norm
+        weights as they are NOW, so that re-loaded weights can never run under a stale bound)."""
         P = self._packed
         ops.sigma_embedding(sigma_dev, self.affline_norm.weight, ws["e"], ws["emb"])
         ops.gemv(self.t_embedder["1"].linear_1.weight, ws["e"], out=ws["t1"])
         ops.gemv(self.t_embedder["1"].linear_2.weight, ws["t1"], out=ws["lora"], act=1)
         ops.gemv_batched(P["mod_a"], ws["emb"], ws["mod_h"], act=1)
         ops.gemv_batched(P["mod_b"], ws["mod_h"], ws["mod"], add=ws["lora"])
+        ops.qk_logit_bound(P["qn"], P["kn"], out=ws["qk_bound"])
 
     def stage_embed(self, ws) -> None:
         ops.gemm(ws["tok"], self._packed["wx"], out=ws["x"])
@@ -327,10 +341,12 @@ class CleanGeneralDIT(nn.Module):
     def stage_pre_attention(self, ws, i: int) -> None:
         """AdaLN -> fused QKV GEMM whose epilogue does the per-head RMSNorm + RoPE of q and k (under context parallelism
         it also stores every head's rows straight into the GPU that owns the head: the all-to-all is the epilogue)"""
-        P, D, cp = self._packed, self.model_channels, ws["cp"]
+        P, D, cp, B = self._packed, self.model_channels, ws["cp"], ws["B"]
         m_sa = ws["mod"][3 * i]
         ops.adaln_modulate(ws["x"], m_sa[:D], m_sa[D:2 * D], out=ws["xm"])
         if not self.fuse_qkv_epilogue:
+            if B > 1 and cp is not None:
+                raise ValueError("the stand-alone scatter kernel (A/B reference) handles one sequence; use fuse_qkv_epilogue")
             qkv = ws.get("qkv")
             if qkv is None:
                 qkv = ws["qkv"] = torch.empty(ws["S"], 3 * D, device=ws["x"].device, dtype=BF16)
@@ -344,22 +360,26 @@ class CleanGeneralDIT(nn.Module):
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], out=ws["qkv"])
         else:
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], peer_ptrs=ws["a2a_ptrs"],
-                                   peer_ld=3 * D // cp.world, row0=cp.rank * ws["S"])
+                                   peer_ld=3 * B * D // cp.world, row0=cp.rank * ws["S"], batch=B)
 
     def stage_attention(self, ws, i: int, timers: Optional[list] = None) -> None:
-        D, Hh, cp = self.model_channels, self.num_heads, ws["cp"]
+        D, Hh, cp, B, S = self.model_channels, self.num_heads, ws["cp"], ws["B"], ws["S"]
+        bound = ws["qk_bound"][i:i + 1]
         if timers is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         if cp is None:
-            qkv = ws["qkv"]
-            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Hh, out=ws["attn"])
+            for b in range(B):
+                qkv = ws["qkv"][b * S:(b + 1) * S]
+                ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Hh, out=ws["attn"][b * S:(b + 1) * S], max_abs_logit=bound)
         elif cp.mode == "ring":
             self._ring_attention(ws)
         else:
-            Dp, a2a = D // cp.world, ws["a2a"]
-            ops.attention_cp(a2a[:, :Dp], a2a[:, Dp:2 * Dp], a2a[:, 2 * Dp:], Hh // cp.world, ws["attn_ptrs"], D, ws["S"],
-                             cp.rank * Dp)
+            # (sequence, local head) pairs are the attention problems of this rank: B * H/P "heads" over all S tokens
+            Hp, a2a = Hh // cp.world, ws["a2a"]
+            w = B * Hp * 128
+            ops.attention_cp(a2a[:, :w], a2a[:, w:2 * w], a2a[:, 2 * w:], B * Hp, ws["attn_ptrs"], D, S, cp.rank * Hp * 128,
+                             heads_per_batch=Hp, batch_rows=S, max_abs_logit=bound)
         if timers is not None:
             ev[1].record()
             timers.append(ev)
@@ -395,12 +415,14 @@ class CleanGeneralDIT(nn.Module):
 
     def stage_post_attention(self, ws, i: int, use_ca: bool) -> None:
         """out-projection with gated residual; cross-attention vector + AdaLN; MLP with gated residual"""
-        P, D = self._packed, self.model_channels
+        P, D, B, S = self._packed, self.model_channels, ws["B"], ws["S"]
         x, xm, h, mod = ws["x"], ws["xm"], ws["h"], ws["mod"]
         m_sa, m_ca, m_mlp = mod[3 * i], mod[3 * i + 1], mod[3 * i + 2]
         ops.gemm(ws["attn"], P["wo"][i], out=x, epilogue=_lib.EPI_GATED_RESIDUAL, resid=x, gate=m_sa[2 * D:])
-        if use_ca:
-            ops.adaln_modulate(x, m_mlp[:D], m_mlp[D:2 * D], out=xm, add_gate=m_ca[2 * D:], add_vec=ws["ca_vec"][i])
+        if use_ca:      # the cross-attention vector is the only per-sequence term of a block
+            for b in range(B):
+                ops.adaln_modulate(x[b * S:(b + 1) * S], m_mlp[:D], m_mlp[D:2 * D], out=xm[b * S:(b + 1) * S],
+                                   add_gate=m_ca[2 * D:], add_vec=ws["ca_vec"][b, i])
         else:
             ops.adaln_modulate(x, m_mlp[:D], m_mlp[D:2 * D], out=xm)
         ops.gemm(xm, P["w1"][i], out=h, epilogue=_lib.EPI_GELU)
@@ -414,8 +436,8 @@ class CleanGeneralDIT(nn.Module):
         return ws["y"]
 
     def run_blocks(self, ws, use_ca: bool, timers: Optional[list] = None) -> torch.Tensor:
-        """tokens -> y [S, 64].  Consumes ws['tok'] / ws['mod'] / ws['ca_vec'].
-        `timers` (bench only): a list that receives one (start, end) CUDA-event pair per attention launch.
+        """tokens -> y [B*S, 64].  Consumes ws['tok'] / ws['mod'] / ws['ca_vec'].
+        `timers` (bench only): a list that receives one (start, end) CUDA-event pair per attention stage.
         Under context parallelism the two device-side barriers per block order the P2P stores of the fused exchange:
         q/k/v rows must have landed before the attention reads them, its output rows before the out-projection."""
         cp = ws["cp"]
@@ -431,13 +453,24 @@ class CleanGeneralDIT(nn.Module):
         return self.stage_final(ws)
 
     def denoise_step(self, ws, x: torch.Tensor, sigma: torch.Tensor, sigma_next: torch.Tensor, use_ca: bool,
-                     timers: Optional[list] = None) -> None:
-        """One guidance-free EDM Euler step in place on x [16,T,H,W] (model_diffusion_renderer.py:224-234): sigma-only
-        vectors, c_in scale + patchify, the transformer, unpatchify + Euler.  sigma / sigma_next: fp32 device scalars."""
+                     timers: Optional[list] = None, guidance: float = 0.0) -> None:
+        """One EDM Euler step in place on x [16,T,H,W] or [N,16,T,H,W] (model_diffusion_renderer.py:224-234): sigma-only
+        vectors, c_in scale + patchify, ONE transformer pass over all sequences of the workspace, unpatchify (+ CFG) +
+        Euler.  Guidance 0: the workspace holds N sequences (one per latent).  Guidance > 0: 2N sequences, the N
+        conditional ones first, each latent feeding its cond and its uncond sequence (:230-232 as one batched forward).
+        sigma / sigma_next: fp32 device scalars."""
+        xs = x if x.ndim == 5 else x.unsqueeze(0)
+        N, B, S = xs.shape[0], ws["B"], ws["S"]
+        if B != (2 * N if guidance > 0 else N):
+            raise ValueError(f"workspace holds {B} sequences, the step needs {2 * N if guidance > 0 else N}")
         self.modulation(ws, sigma)
-        ops.scale_patchify(x, sigma, ws["tok"])
+        for b in range(B):
+            ops.scale_patchify(xs[b % N], sigma, self._rows(ws, "tok", b))
         y = self.run_blocks(ws, use_ca, timers)
-        ops.unpatchify_euler(y, None, 0.0, sigma, sigma_next, x, x)
+        for n in range(N):
+            y_c = y[n * S:(n + 1) * S]
+            y_u = y[(N + n) * S:(N + n + 1) * S] if guidance > 0 else None
+            ops.unpatchify_euler(y_c, y_u, guidance, sigma, sigma_next, xs[n], xs[n])
 
     def _check_input(self, x: torch.Tensor) -> Tuple[int, int, int]:
         if x.ndim != 5:
@@ -497,8 +530,11 @@ class CleanDiffusionRendererGeneralDIT(CleanGeneralDIT):
             return None
         if context_index is None:
             raise TypeError("forward() missing required argument 'context_index' (inverse renderer)")
-        idx = int(torch.as_tensor(context_index).reshape(-1)[0].item())   # the reference casts bf16 -> long (:736)
-        return self.context_embedding.weight[idx]
+        # device-side lookup (no .item(): the public forward must not synchronise with the host); the reference casts
+        # bf16 -> long (:736)
+        w = self.context_embedding.weight
+        idx = torch.as_tensor(context_index).reshape(-1)[:1].to(device=w.device, non_blocking=True).long()
+        return w.index_select(0, idx)[0]
 
     def forward(self, x, timesteps, latent_condition, context_index=None, **kwargs):
         return super().forward(x=x, timesteps=timesteps, crossattn_emb=self.context_token(context_index),

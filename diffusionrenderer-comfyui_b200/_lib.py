@@ -58,6 +58,12 @@ PROTOTYPES = {
                                 c_int, c_void_p],
     "drb_gemm_qkv_norm_rope": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, POINTER(c_void_p), c_int, c_int64, c_int, c_void_p],
+    "drb_gemm_qkv_norm_rope_batched": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int, c_void_p],
+    "drb_attention_bf16_bounded": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p],
+    "drb_qk_logit_bound": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "drb_attention_bf16_cp_batched": [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int,
+                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "drb_attention_bf16_cp": [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int, c_int,
                               c_int, c_void_p],
     "drb_cp_qk_norm_rope_scatter": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p), c_int,

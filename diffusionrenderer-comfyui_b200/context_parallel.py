@@ -51,12 +51,13 @@ def head_owner(head: int, num_heads: int, world: int) -> Tuple[int, int]:
 
 
 def gather_frames(x_local: torch.Tensor, group=None) -> torch.Tensor:
-    """[C, T/P, H, W] per rank -> [C, T, H, W] on every rank, frames in rank order (3.6 MB at 57x704x1280, once per pass)"""
+    """[..., T/P, H, W] per rank -> [..., T, H, W] on every rank, frames in rank order (3.6 MB per pass at 57x704x1280,
+    once per sampler run)"""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     parts = [torch.empty_like(x_local) for _ in range(world)]
     dist.all_gather(parts, x_local.contiguous(), group=group)
-    return torch.cat(parts, dim=1)
+    return torch.cat(parts, dim=-3)
 
 
 class _RawTensor:

@@ -9,9 +9,15 @@
 //   warp 2        TMEM allocator (all 512 columns: S_0 | S_1 | O_0 | O_1, each 128 fp32 columns; P_t aliases S_t)
 //   warps 4..7    softmax warpgroup of tile 0 (one query row per thread)
 //   warps 8..11   softmax warpgroup of tile 1
-// While warpgroup t exponentiates S_t(j), the tensor pipe runs P V and Q K^T of the other tile.  The softmax reference is
-// lazy and max-free: tile 0 fixes it at the exact row maximum, later it moves (and O_t, in TMEM, is rescaled by the owning
-// softmax thread between s_full and p_full, when O_t is quiescent) only after a tile whose row sum reached 2^8.
+// While warpgroup t exponentiates S_t(j), the tensor pipe runs P V and Q K^T of the other tile.  Two softmax flavours,
+// chosen per launch by a uniform branch on a device-resident certificate (so no host synchronisation is needed to pick):
+//   certified  the reference is lazy and max-free: tile 0 fixes it at the exact row maximum, later it moves (and O_t, in
+//              TMEM, is rescaled by the owning softmax thread between s_full and p_full, when O_t is quiescent) only after
+//              a tile whose row sum reached 2^8.  Exact whenever the logits are bounded: the caller passes a device float
+//              B with |q.k| / sqrt(128) <= B (the DiT computes it from its q/k RMSNorm weights, drb_qk_logit_bound); for
+//              B <= kMaxCertifiedLogit, 2^(x - M) cannot overflow however the keys are ordered.
+//   safe       a per-tile row maximum moves the reference whenever a logit exceeds it by more than 2^8 — the general
+//              form for unbounded logits (no certificate, or B too large), a few percent slower.
 //
 // Roofline: tensor pipe, 4*q_len*kv_len*128 flop per head.
 #include <stdlib.h>
@@ -33,6 +39,9 @@ constexpr int kKvSlots = 5;
 constexpr int kAttnThreads = 384;
 constexpr int kAttnSmem = kQTilesPerCta * kTileBytes + kKvSlots * kTileBytes + 1024 + 256;
 constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // log2(e) / sqrt(128)
+// |q.k| / sqrt(128) bound (natural units) up to which the max-free softmax is provably overflow-free: the reference sits at
+// tile 0's row maximum M0 >= -B log2(e) and only ever moves up, so x = s*c - M <= 2 B log2(e) <= 113 < 127 for B <= 39.
+constexpr float kMaxCertifiedLogit = 39.0f;
 
 struct AttnParams {
   // output row r goes to o_peers[r / rows_per_rank] at local row r % rows_per_rank, column col0 + head*128: a single
@@ -41,6 +50,13 @@ struct AttnParams {
   int64_t ld_o;
   int q_len, kv_len;
   int rows_per_rank, col0;
+  // batched sequences (cp only): "head" index = b * heads_per_batch + h; sequence b's rows start at local row b * batch_rows
+  // of the destination and its head h sits at column col0 + h*128.  Unbatched: heads_per_batch = num_heads.
+  int heads_per_batch, batch_rows;
+  // certificate of the max-free softmax: device float B >= |q.k| / sqrt(128) (NULL = none); force_safe: 1 always the
+  // per-tile-max softmax, 0 by certificate, -1 never (tuning only)
+  const float* logit_bound;
+  int force_safe;
   // ring form (drb_attention_bf16_ring): this launch is one K/V block of a longer key sequence.  The running state per
   // (row, head) — reference m (log2 domain), sum l, un-normalised fp32 output — lives in ring_ml [q_len, H, 2] and ring_o
   // [q_len, H*128]; the epilogue merges this block into it and, on the last block, writes the normalised bf16 rows.
@@ -324,6 +340,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // MUFU alone, is what bounds the softmax: tools/ubench), and a tile's P may exceed 2^8 only by the growth inside
     // that one tile, which the fp32 / bf16 exponent absorbs.
     float M = 0.f, l = 0.f, prev_sum = 0.f;
+    const bool safe = p.force_safe > 0 ||
+                      (p.force_safe == 0 && (p.logit_bound == nullptr || !(__ldg(p.logit_bound) <= kMaxCertifiedLogit)));
     PROF_DECL;
     for (int j = 0; j < n_kv; ++j) {
       PROF(0);
@@ -334,19 +352,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tmem_ld32(s_tmem, s0);
       tmem_ld32(s_tmem + 32, s1);
       const int valid = p.kv_len - j * kTileKV;    // >= 128 except on a ragged last tile
-      if (j == 0) {
+      if (safe || j == 0) {
         tmem_ld32(s_tmem + 64, s2);
         tmem_ld32(s_tmem + 96, s3);
         tmem_wait_ld();
         float mx = -INFINITY;
+        if (valid >= kTileKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < valid) mx = fmaxf(mx, __uint_as_float(s0[i]));
-          if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(s1[i]));
-          if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(s2[i]));
-          if (96 + i < valid) mx = fmaxf(mx, __uint_as_float(s3[i]));
+          for (int i = 0; i < 32; i += 2) {
+            mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));   // ptxas fuses these into 3-input FMNMX
+            mx = fmaxf(mx, fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
+            mx = fmaxf(mx, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s2[i + 1])));
+            mx = fmaxf(mx, fmaxf(__uint_as_float(s3[i]), __uint_as_float(s3[i + 1])));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < valid) mx = fmaxf(mx, __uint_as_float(s0[i]));
+            if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(s1[i]));
+            if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(s2[i]));
+            if (96 + i < valid) mx = fmaxf(mx, __uint_as_float(s3[i]));
+          }
         }
-        M = mx * kScaleLog2;
+        const float m_tile = mx * kScaleLog2;
+        if (j == 0) {
+          M = m_tile;
+        } else {
+          // safe: move the reference only when this tile holds a logit more than 2^8 above it (then x <= 8 always)
+          const bool need = m_tile - M > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? ex2(M - m_tile) : 1.0f;
+            if (need) M = m_tile;
+            l *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(o_tmem + c * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o_tmem + c * 32, o);
+            }
+            tmem_wait_st();
+          }
+        }
       } else {
         const bool grow = !(prev_sum < 256.0f);
         if (__any_sync(0xffffffffu, grow)) {
@@ -425,8 +474,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __nv_bfloat16* dst = nullptr;
     if (row < p.q_len) {
       const int owner = row / p.rows_per_rank;
-      dst = static_cast<__nv_bfloat16*>(p.o_peers[owner]) + static_cast<int64_t>(row - owner * p.rows_per_rank) * p.ld_o + p.col0 +
-            head * kHeadDim;
+      const int b = head / p.heads_per_batch, hl = head - b * p.heads_per_batch;
+      dst = static_cast<__nv_bfloat16*>(p.o_peers[owner]) +
+            (static_cast<int64_t>(b) * p.batch_rows + row - owner * p.rows_per_rank) * p.ld_o + p.col0 + hl * kHeadDim;
     }
     if (p.ring_o == nullptr) {
       const float inv_l = 1.0f / l;
@@ -508,17 +558,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }  // namespace
 }  // namespace drb
 
+namespace drb {
+namespace {
+struct AttnLaunchExtra {
+  float* ring_o = nullptr;
+  float* ring_ml = nullptr;
+  int ring_first = 0, ring_last = 0;
+  int heads_per_batch = 0, batch_rows = 0;   // 0: unbatched
+  const float* logit_bound = nullptr;        // the caller's certificate (device float); NULL = none (safe softmax)
+};
+
+template <uint32_t kMask>
+int attention_configure() {
+  DRB_CUDA(cudaFuncSetAttribute(attention_kernel<kMask, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+  DRB_CUDA(cudaFuncSetAttribute(attention_kernel<kMask, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+  return 0;
+}
+
+template <uint32_t kMask>
+int attention_dispatch(const cudaLaunchConfig_t& cfg, bool pair, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const AttnParams& p) {
+  static DeviceOnce configured;   // per mask and per device: the attribute belongs to the device's context
+  const int rc = device_once(configured, [] { return attention_configure<kMask>(); });
+  if (rc) return rc;
+  if (pair) DRB_CUDA(cudaLaunchKernelEx(&cfg, attention_kernel<kMask, true>, tq, tk, tv, p));
+  else DRB_CUDA(cudaLaunchKernelEx(&cfg, attention_kernel<kMask, false>, tq, tk, tv, p));
+  return 0;
+}
+}  // namespace
+}  // namespace drb
+
 static int attention_launch(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
                             int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0, void* stream,
-                            float* ring_o = nullptr, float* ring_ml = nullptr, int ring_first = 0, int ring_last = 0) {
+                            const drb::AttnLaunchExtra& ex = drb::AttnLaunchExtra()) {
   using namespace drb;
   DRB_REQUIRE(q && k && v && o_peers, "null pointer");
   DRB_REQUIRE(q_len > 0 && kv_len > 0 && num_heads > 0, "q_len, kv_len, num_heads must be positive");
   DRB_REQUIRE(ld_qkv % 8 == 0 && ld_o % 8 == 0 && col0 % 8 == 0 && col0 >= 0, "row pitches / column offset must be multiples of 8 elements");
-  DRB_REQUIRE(ld_qkv >= static_cast<int64_t>(num_heads) * kHeadDim && ld_o >= col0 + static_cast<int64_t>(num_heads) * kHeadDim,
-              "row pitch smaller than num_heads * 128");
+  const int hpb = ex.heads_per_batch > 0 ? ex.heads_per_batch : num_heads;
+  DRB_REQUIRE(num_heads % hpb == 0 && ex.batch_rows >= 0, "heads_per_batch must divide the head count");
+  DRB_REQUIRE(ld_qkv >= static_cast<int64_t>(num_heads) * kHeadDim && ld_o >= col0 + static_cast<int64_t>(hpb) * kHeadDim,
+              "row pitch smaller than the heads it holds");
   DRB_REQUIRE(world >= 1 && world <= DRB_CP_MAX_RANKS && rows_per_rank > 0 &&
                   static_cast<int64_t>(rows_per_rank) * world >= q_len, "rows_per_rank * world must cover q_len");
+  DRB_REQUIRE((reinterpret_cast<uintptr_t>(ex.logit_bound) & 3) == 0, "logit bound pointer misaligned");
   AttnParams p{};
   for (int i = 0; i < world; ++i) {
     DRB_REQUIRE(o_peers[i] != nullptr && (reinterpret_cast<uintptr_t>(o_peers[i]) & 15) == 0, "o not 16-byte aligned");
@@ -529,44 +612,31 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
   p.kv_len = kv_len;
   p.rows_per_rank = rows_per_rank;
   p.col0 = col0;
-  p.ring_o = ring_o;
-  p.ring_ml = ring_ml;
-  p.ring_first = ring_first;
-  p.ring_last = ring_last;
+  p.heads_per_batch = hpb;
+  p.batch_rows = ex.batch_rows;
+  p.ring_o = ex.ring_o;
+  p.ring_ml = ex.ring_ml;
+  p.ring_first = ex.ring_first;
+  p.ring_last = ex.ring_last;
   p.num_heads = num_heads;
+  // DRB_ATTN_PAIR (0 = no K/V multicast) and DRB_ATTN_SAFE (1 = always the per-tile-max softmax, 0 = never: tuning only)
+  // are A/B switches; the fraction of exponentials on the FMA pipe is fixed at 5/16 (the other fractions
+  // are compiled only with -DDRB_ATTN_TUNE and selected by DRB_ATTN_POLY).
+  static const int pair_ok = [] { const char* e = getenv("DRB_ATTN_PAIR"); return e ? atoi(e) : 1; }();
+  static const int force_safe = [] { const char* e = getenv("DRB_ATTN_SAFE"); return e ? atoi(e) : -1; }();
+  p.logit_bound = ex.logit_bound;
+  p.force_safe = force_safe < 0 ? 0 : (force_safe != 0 ? 1 : -1);
+  dim3 grid((q_len + kTileQ * kQTilesPerCta - 1) / (kTileQ * kQTilesPerCta), num_heads);
+  const bool pair = pair_ok && (grid.x % 2 == 0);       // clusters of two adjacent query blocks of one head
   CUtensorMap tq, tk, tv;
   const uint64_t cols = static_cast<uint64_t>(num_heads) * kHeadDim;
   int rc = make_tmap_2d_bf16(&tq, q, q_len, cols, ld_qkv, kTileQ, 64);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tk, k, kv_len, cols, ld_qkv, kTileKV, 64);
+  // pair: K/V maps with 64-row boxes — each CTA of the pair loads (and multicasts) half of every tile
+  rc = make_tmap_2d_bf16(&tk, k, kv_len, cols, ld_qkv, pair ? kTileKV / 2 : kTileKV, 64);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, kTileKV, 64);
+  rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, pair ? kTileKV / 2 : kTileKV, 64);
   if (rc) return rc;
-  // fraction of the exponentials computed on the FMA pipe; DRB_ATTN_POLY (0 -> 0/16, 1 -> 4/16, 2 -> 5/16, 3 -> 8/16,
-  // 4 -> 3/16, 5 -> 2/16, 6 -> 6/16, 7 -> 7/16) and DRB_ATTN_PAIR (0 = no K/V multicast) are tuning switches only, the
-  // defaults are what was measured fastest on B200.
-  static int variant = -1, pair_ok = 1;
-  if (variant < 0) {
-    const char* e = getenv("DRB_ATTN_POLY");
-    variant = e ? atoi(e) : 2;
-    if (variant < 0 || variant > 7) variant = 2;
-    e = getenv("DRB_ATTN_PAIR");
-    pair_ok = e ? atoi(e) : 1;
-#define DRB_ATTN_CFG(mask)                                                                                                        \
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<mask, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));       \
-    DRB_CUDA(cudaFuncSetAttribute(attention_kernel<mask, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    DRB_ATTN_CFG(0x0000u) DRB_ATTN_CFG(0x1111u) DRB_ATTN_CFG(0x4924u) DRB_ATTN_CFG(0x5555u) DRB_ATTN_CFG(0x0421u) DRB_ATTN_CFG(0x0101u)
-    DRB_ATTN_CFG(0x2929u) DRB_ATTN_CFG(0x52A5u)
-#undef DRB_ATTN_CFG
-  }
-  dim3 grid((q_len + kTileQ * kQTilesPerCta - 1) / (kTileQ * kQTilesPerCta), num_heads);
-  const bool pair = pair_ok && (grid.x % 2 == 0);       // clusters of two adjacent query blocks of one head
-  if (pair) {   // K/V maps with 64-row boxes: each CTA of the pair loads (and multicasts) half of every tile
-    rc = make_tmap_2d_bf16(&tk, k, kv_len, cols, ld_qkv, kTileKV / 2, 64);
-    if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tv, v, kv_len, cols, ld_qkv, kTileKV / 2, 64);
-    if (rc) return rc;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kAttnThreads);
@@ -579,33 +649,51 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#define DRB_ATTN_LAUNCH(mask)                                                                       \
-  if (pair) { DRB_CUDA(cudaLaunchKernelEx(&cfg, attention_kernel<mask, true>, tq, tk, tv, p)); }    \
-  else { DRB_CUDA(cudaLaunchKernelEx(&cfg, attention_kernel<mask, false>, tq, tk, tv, p)); }
-  switch (variant) {
-    case 0: DRB_ATTN_LAUNCH(0x0000u) break;
-    case 1: DRB_ATTN_LAUNCH(0x1111u) break;
-    case 3: DRB_ATTN_LAUNCH(0x5555u) break;
-    case 4: DRB_ATTN_LAUNCH(0x0421u) break;
-    case 5: DRB_ATTN_LAUNCH(0x0101u) break;
-    case 6: DRB_ATTN_LAUNCH(0x2929u) break;
-    case 7: DRB_ATTN_LAUNCH(0x52A5u) break;
-    default: DRB_ATTN_LAUNCH(0x4924u) break;
+#ifdef DRB_ATTN_TUNE
+  static const int variant = [] { const char* e = getenv("DRB_ATTN_POLY"); return e ? atoi(e) : 2; }();
+  switch (variant) {   // 0 -> 0/16, 1 -> 4/16, 2 -> 5/16, 3 -> 8/16, 4 -> 3/16, 5 -> 2/16, 6 -> 6/16, 7 -> 7/16
+    case 0: return attention_dispatch<0x0000u>(cfg, pair, tq, tk, tv, p);
+    case 1: return attention_dispatch<0x1111u>(cfg, pair, tq, tk, tv, p);
+    case 3: return attention_dispatch<0x5555u>(cfg, pair, tq, tk, tv, p);
+    case 4: return attention_dispatch<0x0421u>(cfg, pair, tq, tk, tv, p);
+    case 5: return attention_dispatch<0x0101u>(cfg, pair, tq, tk, tv, p);
+    case 6: return attention_dispatch<0x2929u>(cfg, pair, tq, tk, tv, p);
+    case 7: return attention_dispatch<0x52A5u>(cfg, pair, tq, tk, tv, p);
+    default: break;
   }
-#undef DRB_ATTN_LAUNCH
-  return 0;
+#endif
+  return attention_dispatch<0x4924u>(cfg, pair, tq, tk, tv, p);
 }
 
 extern "C" int drb_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                                   int q_len, int kv_len, int num_heads, void* stream) {
+  return drb_attention_bf16_bounded(q, k, v, ld_qkv, o, ld_o, q_len, kv_len, num_heads, nullptr, stream);
+}
+
+extern "C" int drb_attention_bf16_bounded(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                                          int q_len, int kv_len, int num_heads, const float* max_abs_logit, void* stream) {
   void* peers[1] = {o};
-  return attention_launch(q, k, v, ld_qkv, peers, 1, ld_o, q_len, kv_len, num_heads, 0x7fffffff, 0, stream);
+  drb::AttnLaunchExtra ex;
+  ex.logit_bound = max_abs_logit;
+  return attention_launch(q, k, v, ld_qkv, peers, 1, ld_o, q_len, kv_len, num_heads, 0x7fffffff, 0, stream, ex);
 }
 
 extern "C" int drb_attention_bf16_cp(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
                                      int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0,
                                      void* stream) {
-  return attention_launch(q, k, v, ld_qkv, o_peers, world, ld_o, q_len, kv_len, num_heads, rows_per_rank, col0, stream);
+  return drb_attention_bf16_cp_batched(q, k, v, ld_qkv, o_peers, world, ld_o, q_len, kv_len, num_heads, rows_per_rank, col0, num_heads,
+                                       0, nullptr, stream);
+}
+
+extern "C" int drb_attention_bf16_cp_batched(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers,
+                                             int world, int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank,
+                                             int col0, int heads_per_batch, int batch_rows, const float* max_abs_logit,
+                                             void* stream) {
+  drb::AttnLaunchExtra ex;
+  ex.heads_per_batch = heads_per_batch;
+  ex.batch_rows = batch_rows;
+  ex.logit_bound = max_abs_logit;
+  return attention_launch(q, k, v, ld_qkv, o_peers, world, ld_o, q_len, kv_len, num_heads, rows_per_rank, col0, stream, ex);
 }
 
 extern "C" int drb_attention_bf16_ring(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
@@ -616,8 +704,13 @@ extern "C" int drb_attention_bf16_ring(const void* q, const void* k, const void*
   DRB_REQUIRE((reinterpret_cast<uintptr_t>(state_o) & 15) == 0 && (reinterpret_cast<uintptr_t>(state_ml) & 7) == 0, "state buffers misaligned");
   DRB_REQUIRE(!last || o != nullptr, "the last block writes the output");
   void* peers[1] = {o ? o : static_cast<void*>(state_o)};
+  AttnLaunchExtra ex;
+  ex.ring_o = state_o;
+  ex.ring_ml = state_ml;
+  ex.ring_first = first ? 1 : 0;
+  ex.ring_last = last ? 1 : 0;
   return attention_launch(q, k, v, ld_qkv, peers, 1, o ? ld_o : static_cast<int64_t>(num_heads) * kHeadDim, q_len, kv_len, num_heads,
-                          0x7fffffff, 0, stream, state_o, state_ml, first ? 1 : 0, last ? 1 : 0);
+                          0x7fffffff, 0, stream, ex);
 }
 
 #ifdef DRB_ATTN_PROFILE

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
 
 namespace drb {
@@ -26,6 +28,28 @@ int check_cuda(cudaError_t e, const char* where);                // 0 on success
   } while (0)
 
 int num_sms();   // multiprocessor count of the current device (cached)
+
+// One-time kernel configuration PER DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) belongs to the device's
+// context, so a process that drives several GPUs (ComfyUI with more than one device, torch.cuda.set_device switching)
+// must configure every kernel on each of them.  `configure` runs once per device index under a mutex; a launch on
+// another thread waits for it instead of racing ahead with the 48 KB default.
+struct DeviceOnce {
+  std::atomic<uint64_t> done{0};
+  std::mutex mu;
+};
+template <typename F>
+int device_once(DeviceOnce& st, F&& configure) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  if (dev < 0 || dev >= 64) return configure();   // unknown index: configure on every call (cheap, idempotent)
+  const uint64_t bit = 1ull << dev;
+  if (st.done.load(std::memory_order_acquire) & bit) return 0;
+  std::lock_guard<std::mutex> lock(st.mu);
+  if (st.done.load(std::memory_order_relaxed) & bit) return 0;
+  const int rc = configure();
+  if (rc == 0) st.done.fetch_or(bit, std::memory_order_release);
+  return rc;
+}
 
 // ---- TMA descriptors -------------------------------------------------------------------
 // 2-D bf16 row-major tensor [rows][cols] with a row pitch of `ld` elements; box = box_rows x box_cols,

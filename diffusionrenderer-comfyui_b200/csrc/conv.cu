@@ -392,11 +392,11 @@ extern "C" int drb_conv3d_cl(const drb_conv3d_args* a, void* stream) {
   rc = make_tmap_2d_bf16(&maps.w, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cin, static_cast<uint64_t>(taps) * a->Cin,
                          block_n, kBlockK);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    DRB_CUDA(cudaFuncSetAttribute(conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
-    configured = true;
-  }
+  static DeviceOnce configured;   // per device: the attribute belongs to the device's context
+  rc = device_once(configured, [] {
+    return check_cuda(cudaFuncSetAttribute(conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem), "conv3d_kernel smem");
+  });
+  if (rc) return rc;
   ConvParams p{};
   p.T_out = a->T_out; p.H_out = a->H_out; p.W_out = a->W_out;
   p.out_H = a->H_out * a->out_scale; p.out_W = a->W_out * a->out_scale;

@@ -407,6 +407,46 @@ extern "C" int drb_qk_norm_rope(void* qkv, int64_t ld, const void* wq, const voi
   return 0;
 }
 
+// One warp per layer: bound[l] = sqrt(128) * max|wq[l]| * max|wk[l]| * 1.02 (include/drb200.h)
+namespace drb {
+namespace {
+__global__ void __launch_bounds__(32)
+qk_logit_bound_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk, float* __restrict__ bound) {
+  const int l = blockIdx.x, lane = threadIdx.x;
+  float mq = 0.f, mk = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mq = fmaxf(mq, fabsf(__bfloat162float(wq[l * 128 + lane * 4 + i])));
+    mk = fmaxf(mk, fabsf(__bfloat162float(wk[l * 128 + lane * 4 + i])));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, o));
+    mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+  }
+  // NaN weights must not certify anything: fmaxf drops NaNs, so test them explicitly
+  float nan_seen = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = __bfloat162float(wq[l * 128 + lane * 4 + i]), b = __bfloat162float(wk[l * 128 + lane * 4 + i]);
+    if (a != a || b != b) nan_seen = 1.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nan_seen = fmaxf(nan_seen, __shfl_xor_sync(0xffffffffu, nan_seen, o));
+  if (lane == 0) bound[l] = nan_seen > 0.f ? INFINITY : 11.313708498984761f * mq * mk * 1.02f;
+}
+}  // namespace
+}  // namespace drb
+
+extern "C" int drb_qk_logit_bound(const void* wq, const void* wk, float* bound, int layers, void* stream) {
+  using namespace drb;
+  DRB_REQUIRE(wq && wk && bound && layers > 0, "bad arguments");
+  qk_logit_bound_kernel<<<layers, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(wq),
+                                                                            static_cast<const __nv_bfloat16*>(wk), bound);
+  DRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int drb_gemv_bf16_batched(const void* W, int64_t ldw, int64_t w_batch_stride, const void* x,
                                      int64_t x_batch_stride, void* y, int64_t y_batch_stride, const void* add,
                                      int64_t add_batch_stride, int count, int N, int K, int act, void* stream) {

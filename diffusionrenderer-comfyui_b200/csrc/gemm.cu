@@ -64,6 +64,10 @@ struct GemmParams {
   int world, heads_per_rank, row0;
   int64_t peer_ld;
   void* peers[DRB_CP_MAX_RANKS];
+  // batched sequences along M (the five G-buffer passes / cond + uncond of one video): row r belongs to sequence
+  // r / rows_per_batch; under context parallelism sequence b's heads occupy columns (b*heads_per_rank + h)*128 of each
+  // section of the peer row, sections being `batch` times wider.  batch == 1: rows_per_batch = INT_MAX / 2.
+  int rows_per_batch, batch;
 };
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int band_n, int& m, int& n) {
@@ -293,23 +297,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           const int head = head0 + hh;
           const int row_base = row - lane;                          // first row of this warp's 32
-          int64_t dst_pitch;
-          __nv_bfloat16* dst0;
           if (p.world > 0) {
+            // destination row = row0 + (token index inside its sequence); the 32 rows of a warp straddle at most one
+            // sequence boundary (rows_per_batch >= 32), so the sequence index is b0 or b0 + 1
             const int owner = head / p.heads_per_rank;
-            dst_pitch = p.peer_ld;
-            dst0 = static_cast<__nv_bfloat16*>(p.peers[owner]) + static_cast<int64_t>(p.row0 + row_base) * p.peer_ld +
-                   static_cast<int64_t>(sect) * p.heads_per_rank * 128 + (head - owner * p.heads_per_rank) * 128;
-          } else {
-            dst_pitch = p.ldo;
-            dst0 = p.out + static_cast<int64_t>(row_base) * p.ldo + col0 + hh * 128;
-          }
+            const int b0 = row_base / p.rows_per_batch;
+            const int bound = (b0 + 1) * p.rows_per_batch;
+            __nv_bfloat16* dst0 = static_cast<__nv_bfloat16*>(p.peers[owner]) +
+                                  (static_cast<int64_t>(sect) * p.batch + b0) * p.heads_per_rank * 128 +
+                                  (head - owner * p.heads_per_rank) * 128 + (lane & 15) * 8;
 #pragma unroll 4
-          for (int it = 0; it < 16; ++it) {
-            const int rr = it * 2 + (lane >> 4);
-            if (row_base + rr < p.M)
-              *reinterpret_cast<uint4*>(dst0 + rr * dst_pitch + (lane & 15) * 8) =
-                  *reinterpret_cast<const uint4*>(my_stage + rr * 256 + (((lane & 15) ^ (rr & 15)) * 16));
+            for (int it = 0; it < 16; ++it) {
+              const int rr = it * 2 + (lane >> 4);
+              const int grow = row_base + rr;
+              const int nb = grow >= bound ? 1 : 0;
+              if (grow < p.M)
+                *reinterpret_cast<uint4*>(dst0 + static_cast<int64_t>(p.row0 + grow - (b0 + nb) * p.rows_per_batch) * p.peer_ld +
+                                          nb * p.heads_per_rank * 128) =
+                    *reinterpret_cast<const uint4*>(my_stage + rr * 256 + (((lane & 15) ^ (rr & 15)) * 16));
+            }
+          } else {
+            __nv_bfloat16* dst0 = p.out + static_cast<int64_t>(row_base) * p.ldo + col0 + hh * 128;
+#pragma unroll 4
+            for (int it = 0; it < 16; ++it) {
+              const int rr = it * 2 + (lane >> 4);
+              if (row_base + rr < p.M)
+                *reinterpret_cast<uint4*>(dst0 + rr * p.ldo + (lane & 15) * 8) =
+                    *reinterpret_cast<const uint4*>(my_stage + rr * 256 + (((lane & 15) ^ (rr & 15)) * 16));
+            }
           }
           __syncwarp();
         }
@@ -397,10 +412,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   auto kernel = gemm_bf16_kernel<kCtaGroup, kEpi>;
   constexpr int kSmem = Cfg::kSmemBytes + (kEpi == DRB_EPI_QKV_NORM_ROPE ? Cfg::kEpiStageBytes : 4 * 2048);
   static_assert(kSmem <= 232448, "over the 227 KB shared-memory limit of sm_100");
-  static bool configured = false;   // per template instance
-  if (!configured) {
-    DRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
+  static DeviceOnce configured;   // per template instance and per device (the attribute belongs to the device's context)
+  {
+    const int rc = device_once(configured, [&] {
+      return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem), "gemm_bf16_kernel smem");
+    });
+    if (rc) return rc;
   }
   const int tile_m_rows = kBlockM * kCtaGroup;
   const int tiles = ((p.M + tile_m_rows - 1) / tile_m_rows) * ((p.N + kBlockN - 1) / kBlockN);
@@ -444,8 +461,8 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     case DRB_EPI_STORE: return launch_gemm<kCtaGroup, DRB_EPI_STORE>(ta, tb, p, s);
     case DRB_EPI_GELU: return launch_gemm<kCtaGroup, DRB_EPI_GELU>(ta, tb, p, s);
     case DRB_EPI_GATED_RESIDUAL: return launch_gemm<kCtaGroup, DRB_EPI_GATED_RESIDUAL>(ta, tb, p, s);
-    case DRB_EPI_QKV_NORM_ROPE: return launch_gemm<kCtaGroup, DRB_EPI_QKV_NORM_ROPE>(ta, tb, p, s);
-    default: return fail("drb_gemm_bf16", "unknown epilogue");
+    // DRB_EPI_QKV_NORM_ROPE needs the norm weights / RoPE tables of drb_gemm_qkv_norm_rope: not reachable from here
+    default: return fail("drb_gemm_bf16", "epilogue must be DRB_EPI_STORE, DRB_EPI_GELU or DRB_EPI_GATED_RESIDUAL");
   }
 }
 
@@ -498,7 +515,18 @@ extern "C" int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
 extern "C" int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int D,
                                       int K, const void* wq, const void* wk, const void* cos_tab, const void* sin_tab,
                                       void* const* peer_ptrs, int world, int64_t peer_ld, int row0, void* stream) {
+  return drb_gemm_qkv_norm_rope_batched(A, lda, W, ldw, out, ldo, M, D, K, wq, wk, cos_tab, sin_tab, peer_ptrs, world, peer_ld, row0,
+                                        1, M, stream);
+}
+
+extern "C" int drb_gemm_qkv_norm_rope_batched(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M,
+                                              int D, int K, const void* wq, const void* wk, const void* cos_tab,
+                                              const void* sin_tab, void* const* peer_ptrs, int world, int64_t peer_ld, int row0,
+                                              int batch, int rows_per_batch, void* stream) {
   using namespace drb;
+  DRB_REQUIRE(batch >= 1 && rows_per_batch >= 1 && static_cast<int64_t>(batch) * rows_per_batch == M,
+              "batch * rows_per_batch must equal M");
+  DRB_REQUIRE(batch == 1 || rows_per_batch >= 32, "batched sequences need at least 32 rows each");
   DRB_REQUIRE(A && W && wq && wk && cos_tab && sin_tab, "null pointer");
   DRB_REQUIRE(M > 0 && D > 0 && K > 0 && D % 256 == 0 && K % 8 == 0, "D must be a multiple of 256 (two heads per tile), K of 8");
   DRB_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "row pitches must be multiples of 8 elements and cover K");
@@ -512,9 +540,11 @@ extern "C" int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W,
   p.cos_tab = static_cast<const __nv_bfloat16*>(cos_tab);
   p.sin_tab = static_cast<const __nv_bfloat16*>(sin_tab);
   p.sect = D;
+  p.batch = batch;
+  p.rows_per_batch = batch == 1 ? 0x3fffffff : rows_per_batch;
   if (world > 0) {
     DRB_REQUIRE(peer_ptrs != nullptr && world <= DRB_CP_MAX_RANKS && (D / 128) % world == 0 && row0 >= 0, "bad context-parallel arguments");
-    DRB_REQUIRE(peer_ld % 8 == 0 && peer_ld >= 3LL * D / world, "peer row pitch too small");
+    DRB_REQUIRE(peer_ld % 8 == 0 && peer_ld >= 3LL * batch * D / world, "peer row pitch too small");
     for (int i = 0; i < world; ++i) {
       DRB_REQUIRE(peer_ptrs[i] != nullptr && (reinterpret_cast<uintptr_t>(peer_ptrs[i]) & 15) == 0, "bad peer pointer");
       p.peers[i] = peer_ptrs[i];

@@ -457,10 +457,13 @@ extern "C" int drb_haar_patch(const void* x, void* out, int C, int T, int H, int
   const int Tp = (T + 3) / 4, Hp = H / 4, Wp = W / 4;
   DRB_REQUIRE(Hp <= 65535 && Tp <= 65535, "clip too large");
   const size_t smem = static_cast<size_t>(kHaarPix) * (64 * C + 4) * 2;
-  static bool configured = false;
-  if (!configured) {
-    DRB_CUDA(cudaFuncSetAttribute(haar_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaarPix * (64 * kHaarMaxC + 4) * 2));
-    configured = true;
+  static drb::DeviceOnce configured;   // per device: the attribute belongs to the device's context
+  {
+    const int rc = drb::device_once(configured, [] {
+      return drb::check_cuda(cudaFuncSetAttribute(haar_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaarPix * (64 * kHaarMaxC + 4) * 2),
+                             "haar_patch_kernel smem");
+    });
+    if (rc) return rc;
   }
   haar_patch_kernel<<<dim3((Wp + kHaarPix - 1) / kHaarPix, Hp, Tp), kHaarPix, smem, STREAM>>>(CBF(x), BF(out), C, T, H, W);
   DRB_CUDA(cudaGetLastError());
@@ -473,10 +476,13 @@ extern "C" int drb_haar_unpatch(const void* in, void* out, int C, int Tp, int Hp
   DRB_REQUIRE(Tp >= 1 && Hp >= 1 && Wp >= 1 && Hp <= 65535 && Tp <= 65535, "bad dims");
   DRB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "pointers must be 8-byte aligned");
   const size_t smem = static_cast<size_t>(kHaarPix) * (64 * C + 4) * 2;
-  static bool configured = false;
-  if (!configured) {
-    DRB_CUDA(cudaFuncSetAttribute(haar_unpatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaarPix * (64 * kHaarMaxC + 4) * 2));
-    configured = true;
+  static drb::DeviceOnce configured;   // per device: the attribute belongs to the device's context
+  {
+    const int rc = drb::device_once(configured, [] {
+      return drb::check_cuda(cudaFuncSetAttribute(haar_unpatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaarPix * (64 * kHaarMaxC + 4) * 2),
+                             "haar_unpatch_kernel smem");
+    });
+    if (rc) return rc;
   }
   haar_unpatch_kernel<<<dim3((Wp + kHaarPix - 1) / kHaarPix, Hp, Tp), kHaarPix, smem, STREAM>>>(CBF(in), BF(out), C, Tp, Hp, Wp);
   DRB_CUDA(cudaGetLastError());

@@ -9,7 +9,10 @@ nine elementwise tensor ops.  Differences from the reference, all behaviour-pres
     SURVEY.md defect D3) raises a ValueError naming the mismatch instead of a shape error deep inside the net;
   * the dead dynamic-load fallback (it calls a method that does not exist, :227) raises immediately;
   * `shared_conditions()` lets a caller that runs several passes on the same clip (the five G-buffer passes of the
-    inverse node) encode the clip once instead of once per pass (defect D13).
+    inverse node) encode the clip once instead of once per pass (defect D13);
+  * `generate_video_passes()` (no reference counterpart) renders several G-buffer passes of one clip in one sampler
+    run — the passes batched along the token axis of every kernel — which is what the inverse node calls when the
+    pipeline's `batch_passes` is on (default: whenever the net is context-parallel over several GPUs).
 """
 from __future__ import annotations
 
@@ -47,6 +50,10 @@ class CleanDiffusionRendererPipeline:
         self._config_cache: Dict[str, dict] = {}
         self._model_cache: Dict[str, CleanDiffusionRendererModel] = {}
         self._cond_cache: Optional[dict] = None
+        # render the G-buffer passes of a clip as one batched sampler run (generate_video_passes); None = automatic:
+        # on when the net is split over several GPUs (context parallelism), where batching removes the short GEMM waves
+        self.batch_passes: Optional[bool] = None
+        self.output_rank: Optional[int] = 0    # context-parallel runs: the rank that receives host arrays (None = all)
 
     def set_model_type(self, model_type: str):
         new = model_type.lower()
@@ -141,6 +148,51 @@ class CleanDiffusionRendererPipeline:
         video = model.decode(sample)                                   # (B,3,T,H,W) in [-1,1]
         frames = [ops.postprocess_u8(video[b].to(torch.bfloat16).contiguous(), normalize_normal) for b in range(video.shape[0])]
         return torch.stack(frames, dim=0).cpu().numpy()                # uint8 (B,T,H,W,3); the only host sync of the call
+
+    def wants_batched_passes(self) -> bool:
+        if self.batch_passes is not None:
+            return bool(self.batch_passes)
+        model = self.model or self.pre_loaded_model_instance
+        return model is not None and getattr(model.net, "_cp", None) is not None
+
+    def generate_video_passes(self, data_batch: Dict[str, torch.Tensor], context_indices, normalize_normal=None,
+                              seed: int = None) -> list:
+        """`generate_video` for N passes of the inverse renderer over one clip (data_batch without `context_index`):
+        tokenizer encode once, ONE sampler run with the N passes batched along the token axis, then decode + uint8
+        post-process per pass.  Returns a list of N uint8 arrays (B,T,H,W,3) — the same values N generate_video calls
+        return.  Under context parallelism every rank calls this with the same arguments; pass p is decoded by rank
+        p mod P and the frames are delivered to `output_rank` (the other ranks get None entries)."""
+        effective_seed = seed if seed is not None else self.seed
+        context_indices = [int(i) for i in context_indices]
+        flags = list(normalize_normal) if normalize_normal is not None else [False] * len(context_indices)
+        if len(flags) != len(context_indices):
+            raise ValueError("one normalize_normal flag per pass")
+        video_tensor = next((data_batch[k] for k in ("rgb", "image") if k in data_batch), None)
+        if video_tensor is None:
+            raise ValueError("No suitable input tensor for shape inference found in data_batch.")
+        model = self._ensure_model_loaded(tuple(video_tensor.shape))
+        B, _, T, H, W = video_tensor.shape
+        state_shape = [self.config["latent_shape"][0], (T - 1) // 8 + 1, H // 8, W // 8]
+        batch = self._move_to_device({k: v for k, v in data_batch.items() if k != "context_index"})
+        samples = model.generate_samples_multi(batch, context_indices, guidance=self.guidance, seed=effective_seed,
+                                               state_shape=state_shape, num_steps=self.num_steps)
+        cp = getattr(model.net, "_cp", None)
+        world, rank = (cp.world, cp.rank) if cp is not None and hasattr(cp, "group") else (1, 0)
+        frames = []
+        for p, flag in enumerate(flags):
+            if world == 1 or p % world == rank:
+                video = model.decode(samples[p:p + 1])                  # (1,3,T,H,W) in [-1,1]
+                frames.append(ops.postprocess_u8(video[0].to(torch.bfloat16).contiguous(), flag))
+            else:
+                frames.append(torch.empty((T, H, W, 3), device=samples.device, dtype=torch.uint8))
+        if world > 1:
+            import torch.distributed as dist
+            for p, f in enumerate(frames):
+                dist.broadcast(f, src=dist.get_global_rank(cp.group, p % world) if cp.group is not None else p % world, group=cp.group)
+            if self.output_rank is not None and rank != self.output_rank:
+                torch.cuda.current_stream().synchronize()
+                return [None] * len(frames)
+        return [f.unsqueeze(0).cpu().numpy() for f in frames]              # uint8 (1,T,H,W,3) each
 
     def _sample_with_cached_condition(self, model, batch, latent_condition, seed, state_shape):
         with torch.no_grad():

@@ -198,15 +198,55 @@ class CleanDiffusionRendererModel(nn.Module):
             return self.sample_latent(xt, condition.to_dict(), uncondition.to_dict() if guidance > 0 else None,
                                       guidance=guidance, per_step=kwargs.get("per_step"), teacher=kwargs.get("teacher"))
 
-    def sample_latent(self, xt: Tensor, cond: Dict[str, Tensor], uncond: Optional[Dict[str, Tensor]], guidance: float = 0.0,
+    def generate_samples_multi(self, data_batch: Dict, context_indices, guidance: float = 0.0, seed: int = 1000,
+                               state_shape: Tuple = None, num_steps: int = 15, latent_condition: Optional[Tensor] = None) -> Tensor:
+        """N passes over ONE clip that differ only in `context_index` (the inverse node's five G-buffer passes,
+        nodes.py:187-205), sampled together: same seed, same noise and same encoded condition for every pass — exactly what
+        N calls of generate_samples_from_batch compute (:211-235) — but one batched transformer pass per step.
+        Returns (N,16,F,h,w).  `latent_condition`: the already encoded clip, when the caller has it."""
+        with torch.no_grad():
+            torch.manual_seed(seed)
+            if latent_condition is None:
+                self._get_conditions(data_batch)
+                latent_condition = data_batch["latent_condition"]
+            tk = self._get_tensor_kwargs()
+            conds, unconds = [], []
+            for idx in context_indices:
+                ci = torch.full((1, 1), int(idx), dtype=torch.long, device=tk["device"])
+                c, u = self.conditioner.get_condition_uncondition({"latent_condition": latent_condition, "context_index": ci})
+                conds.append(c.to_dict())
+                unconds.append(u.to_dict())
+            self.scheduler.set_timesteps(num_steps, device=tk["device"])
+            xt = torch.randn(size=(1, *state_shape), **tk) * self.scheduler.sigmas[0]
+            return self.sample_latent(xt, conds, unconds if guidance > 0 else None, guidance=guidance)
+
+    def sample_latent(self, xt: Tensor, cond, uncond=None, guidance: float = 0.0,
                       per_step: Optional[list] = None, teacher: Optional[list] = None) -> Tensor:
         """Euler loop on device.  `xt` (1,16,F,h,w) bf16 = noise * sigma_0; scheduler.set_timesteps must have run.
+
+        `cond` / `uncond` are the condition dicts of ONE pass (reference :224-234) or lists of N dicts: N passes over the
+        same clip (the five G-buffer passes of the inverse node differ only in `context_index`) then run as ONE batched
+        transformer pass per step — N sequences stacked along the token-row axis, 2N under CFG (cond and uncond batched,
+        SURVEY.md §8f.1) — instead of N (2N) sequential forwards: every row is computed exactly as in the sequential
+        form (bit-identical results), the weights stream once per step, and under context parallelism the GEMM grids
+        have no short last wave.  Returns (N,16,F,h,w); `xt` may be (1,...) (the same noise for every pass: the node
+        seeds every pass identically, nodes.py:187-205) or (N,...).
         `per_step` collects x_t after every step; `teacher` (one x_t per step) makes the loop teacher-forced — both are
         parity-test hooks."""
         net, sig = self.net, self.scheduler.sigmas
         if xt.dtype != BF16 or not xt.is_cuda:
             raise ValueError("the B200 sampler needs a bfloat16 CUDA latent (no CPU fallback)")
-        T, H, W = net._check_input(xt)
+        conds = list(cond) if isinstance(cond, (list, tuple)) else [cond]
+        N = len(conds)
+        cfg = guidance > 0 and uncond is not None
+        unconds = []
+        if cfg:
+            unconds = list(uncond) if isinstance(uncond, (list, tuple)) else [uncond]
+            if len(unconds) != N:
+                raise ValueError("one unconditional dict per conditional dict")
+        if xt.ndim != 5 or xt.shape[0] not in (1, N):
+            raise ValueError(f"xt must be (1 or {N}, C, T, H, W), got {tuple(xt.shape)}")
+        T, H, W = net._check_input(xt[:1])
         net._ensure_packed()
         # context parallelism (net.enable_context_parallel): this rank owns latent frames [t0, t1); the Euler update is
         # token-local, so the latent stays sharded through the whole loop and is gathered once at the end
@@ -216,39 +256,27 @@ class CleanDiffusionRendererModel(nn.Module):
             from .context_parallel import shard_frames
             t0, t1 = shard_frames(T, cp.rank, cp.world)
         Tl = t1 - t0
-        ws = net._workspace(Tl, H, W, xt.device, cp)
+        seqs = conds + unconds
+        ws = net._workspace(Tl, H, W, xt.device, cp, batch=len(seqs))
         sig = sig.to(device=xt.device, dtype=torch.float32).contiguous()
 
         def local(t5: Optional[Tensor]) -> Optional[Tensor]:
             return None if t5 is None else t5[:, :, t0:t1]
 
         def full(x_local: Tensor) -> Tensor:
-            return (x_local if cp is None else cp.all_gather_frames(x_local)).unsqueeze(0)
+            return x_local if cp is None else cp.all_gather_frames(x_local)
 
-        x = local(xt)[0].contiguous().clone()
+        # constants of the passes, hoisted out of the step loop
+        use_ca = False
+        for b, c in enumerate(seqs):
+            net.prepare_condition(ws, local(c.get("latent_condition")), Tl, H, W, b)
+            use_ca = net.prepare_context(ws, net.context_token(c.get("context_index")), b)
+        x = local(xt).expand(N, -1, -1, -1, -1).contiguous().clone()
         n = sig.numel() - 1
-        passes = [cond] if uncond is None else [cond, uncond]
-        ctx = [net.context_token(c.get("context_index")) for c in passes]
-        y_c = torch.empty_like(ws["y"]) if uncond is not None else None
-        if uncond is None:   # constants of the pass, hoisted out of the step loop
-            net.prepare_condition(ws, local(cond.get("latent_condition")), Tl, H, W)
-            use_ca = net.prepare_context(ws, ctx[0])
         for i in range(n):
             if teacher is not None:
-                x = local(teacher[i])[0].contiguous().clone()
-            s_i, s_n = sig[i:i + 1], sig[i + 1:i + 2]
-            if uncond is None:
-                net.denoise_step(ws, x, s_i, s_n, use_ca)
-            else:
-                net.modulation(ws, s_i)
-                for k, c in enumerate(passes):
-                    net.prepare_condition(ws, local(c.get("latent_condition")), Tl, H, W)
-                    use_ca = net.prepare_context(ws, ctx[k])
-                    ops.scale_patchify(x, s_i, ws["tok"])
-                    y = net.run_blocks(ws, use_ca)
-                    if k == 0:
-                        y_c.copy_(y)
-                ops.unpatchify_euler(y_c, y, guidance, s_i, s_n, x, x)
+                x = local(teacher[i]).expand(N, -1, -1, -1, -1).contiguous().clone()
+            net.denoise_step(ws, x, sig[i:i + 1], sig[i + 1:i + 2], use_ca, guidance=guidance if cfg else 0.0)
             if per_step is not None:
                 per_step.append(full(x).clone())
         return full(x)

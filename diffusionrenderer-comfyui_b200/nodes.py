@@ -116,16 +116,29 @@ class Cosmos1InverseRenderer:
         except Exception:
             pbar = None
         outputs = {}
+
+        def keep(name, arr):
+            if arr is None:            # a helper rank of a context-parallel group: the frames went to the output rank
+                outputs[name] = None
+                return
+            out = torch.from_numpy(arr).float() / 255.0
+            b, t, h, w, c = out.shape
+            outputs[name] = out.reshape(b * t, h, w, c)
+            if pbar is not None:
+                pbar.update(1)
+
+        if getattr(pipeline, "wants_batched_passes", lambda: False)() and clip.shape[0] == 1:
+            # one sampler run for all five passes (batched along the token axis); same values as the loop below
+            arrs = pipeline.generate_video_passes({"rgb": clip, "video": clip}, [GBUFFER_INDEX_MAPPING[n] for n in INFERENCE_PASSES],
+                                                  normalize_normal=[n == "normal" for n in INFERENCE_PASSES], seed=seed)
+            for name, arr in zip(INFERENCE_PASSES, arrs):
+                keep(name, arr)
+            return tuple(outputs[n] for n in INFERENCE_PASSES)
         with pipeline.shared_conditions():                               # the clip is tokenised once for all five passes
             for name in INFERENCE_PASSES:
                 batch = {"rgb": clip, "video": clip,
                          "context_index": torch.full((clip.shape[0], 1), GBUFFER_INDEX_MAPPING[name], dtype=torch.long)}
-                arr = pipeline.generate_video(data_batch=batch, normalize_normal=(name == "normal"), seed=seed)
-                out = torch.from_numpy(arr).float() / 255.0
-                b, t, h, w, c = out.shape
-                outputs[name] = out.reshape(b * t, h, w, c)
-                if pbar is not None:
-                    pbar.update(1)
+                keep(name, pipeline.generate_video(data_batch=batch, normalize_normal=(name == "normal"), seed=seed))
         return tuple(outputs[n] for n in INFERENCE_PASSES)
 
 

@@ -56,8 +56,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, e
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [Sq, H*128], k/v [Skv, H*128] (row-strided views of one qkv buffer are fine, same pitch) -> o [Sq, H*128]."""
+              out: Optional[torch.Tensor] = None, max_abs_logit: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [Sq, H*128], k/v [Skv, H*128] (row-strided views of one qkv buffer are fine, same pitch) -> o [Sq, H*128].
+    `max_abs_logit`: fp32 device scalar, the caller's bound on |q.k|/sqrt(128); None = unknown (per-tile-max softmax)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, n)
     ld = _rows2d(q, "q")
@@ -66,8 +67,27 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int,
     if out is None:
         out = torch.empty((q.shape[0], num_heads * 128), device=q.device, dtype=BF16)
     _req(out, "out")
-    _lib.call("drb_attention_bf16", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), _rows2d(out, "out"),
-              q.shape[0], k.shape[0], num_heads, _stream())
+    _lib.call("drb_attention_bf16_bounded", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), _rows2d(out, "out"),
+              q.shape[0], k.shape[0], num_heads, _bound_ptr(max_abs_logit), _stream())
+    return out
+
+
+def _bound_ptr(b: Optional[torch.Tensor]) -> Optional[int]:
+    if b is None:
+        return None
+    _req(b, "max_abs_logit", torch.float32)
+    return b.data_ptr()
+
+
+def qk_logit_bound(wq: torch.Tensor, wk: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wq, wk [L,128] bf16 per-head RMSNorm weights -> fp32 [L] bounds on |q.k|/sqrt(128) (Cauchy-Schwarz)"""
+    _req(wq, "wq"), _req(wk, "wk")
+    if wq.shape != wk.shape or wq.shape[-1] != 128 or not wq.is_contiguous() or not wk.is_contiguous():
+        raise ValueError("wq, wk must be contiguous [L, 128]")
+    L = wq.numel() // 128
+    if out is None:
+        out = torch.empty((L,), device=wq.device, dtype=torch.float32)
+    _lib.call("drb_qk_logit_bound", wq.data_ptr(), wk.data_ptr(), out.data_ptr(), L, _stream())
     return out
 
 
@@ -330,15 +350,18 @@ def qk_norm_rope_scatter(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, 
 
 
 def attention_cp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, o_ptrs, ld_o: int, rows_per_rank: int,
-                 col0: int) -> None:
-    """attention over the local heads and all tokens; output row r is stored to o_ptrs[r // rows_per_rank]"""
+                 col0: int, heads_per_batch: Optional[int] = None, batch_rows: int = 0,
+                 max_abs_logit: Optional[torch.Tensor] = None) -> None:
+    """attention over the local heads and all tokens; output row r is stored to o_ptrs[r // rows_per_rank].  Batched
+    sequences: `num_heads` = batch * heads_per_batch (b, h) pairs; sequence b lands at local row b * batch_rows + ..."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, n)
     ld = _rows2d(q, "q")
     if _rows2d(k, "k") != ld or _rows2d(v, "v") != ld:
         raise ValueError("q, k, v must share one row pitch")
-    _lib.call("drb_attention_bf16_cp", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _lib.ptr_array(o_ptrs), len(o_ptrs), ld_o,
-              q.shape[0], k.shape[0], num_heads, rows_per_rank, col0, _stream())
+    _lib.call("drb_attention_bf16_cp_batched", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _lib.ptr_array(o_ptrs), len(o_ptrs), ld_o,
+              q.shape[0], k.shape[0], num_heads, rows_per_rank, col0, num_heads if heads_per_batch is None else heads_per_batch,
+              batch_rows, _bound_ptr(max_abs_logit), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ environment maps (fp32)
@@ -377,9 +400,10 @@ def envmap_tonemap(img: torch.Tensor, H: int, W: int):
 
 def qkv_gemm_norm_rope(a: torch.Tensor, w: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos_tab: torch.Tensor,
                        sin_tab: torch.Tensor, out: Optional[torch.Tensor] = None, peer_ptrs=None, peer_ld: int = 0,
-                       row0: int = 0) -> Optional[torch.Tensor]:
+                       row0: int = 0, batch: int = 1) -> Optional[torch.Tensor]:
     """[q | k | v] = a[M,K] @ w[3D,K]^T with per-head RMSNorm + RoPE of q, k in the GEMM epilogue.  Plain: rows go to
-    out [M, 3D].  Context-parallel (`peer_ptrs`): head h's rows go to peer_ptrs[h // (H/P)] at row row0 + s (no `out`)."""
+    out [M, 3D].  Context-parallel (`peer_ptrs`): head h's rows go to peer_ptrs[h // (H/P)] at row row0 + s (no `out`).
+    `batch` sequences of M / batch rows each are stacked along M (cos/sin tables repeated per sequence)."""
     for t, n in ((a, "a"), (w, "w"), (wq, "wq"), (wk, "wk"), (cos_tab, "cos_tab"), (sin_tab, "sin_tab")):
         _req(t, n)
     M, K = a.shape
@@ -396,9 +420,11 @@ def qkv_gemm_norm_rope(a: torch.Tensor, w: torch.Tensor, wq: torch.Tensor, wk: t
                   _rows2d(out, "out"), M, D, K, wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), None, 0, 0, 0,
                   _stream())
         return out
-    _lib.call("drb_gemm_qkv_norm_rope", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), None, 0, M, D, K,
+    if M % batch:
+        raise ValueError("the rows do not split into `batch` equal sequences")
+    _lib.call("drb_gemm_qkv_norm_rope_batched", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), None, 0, M, D, K,
               wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), _lib.ptr_array(peer_ptrs), len(peer_ptrs),
-              peer_ld, row0, _stream())
+              peer_ld, row0, batch, M // batch, _stream())
     return None
 
 

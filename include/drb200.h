@@ -67,6 +67,16 @@ int drb_attention_bf16_ring(const void* q, const void* k, const void* v, int64_t
 int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int D,
                            int K, const void* wq, const void* wk, const void* cos_tab, const void* sin_tab,
                            void* const* peer_ptrs, int world, int64_t peer_ld, int row0, void* stream);
+/* The same with `batch` independent token sequences stacked along M (row r belongs to sequence r / rows_per_batch): the
+ * five G-buffer passes of one clip (nodes.py:187-205) or cond + uncond under CFG (model_diffusion_renderer.py:230-232) run
+ * as ONE GEMM, so the weights stream once per batch and the tile grid has no short last wave at M = S/P.  cos_tab /
+ * sin_tab are [M,128] (the per-sequence table repeated).  world > 0: sequence b, head h, token s goes to row row0 + s of
+ * the owner's [S, peer_ld] buffer at column (sect*batch + b)*(H/world)*128 + (h mod H/world)*128, sect = 0 q, 1 k, 2 v —
+ * i.e. (b, h) pairs look like batch*(H/world) heads to drb_attention_bf16_cp_batched.  rows_per_batch >= 32. */
+int drb_gemm_qkv_norm_rope_batched(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int D,
+                                   int K, const void* wq, const void* wk, const void* cos_tab, const void* sin_tab,
+                                   void* const* peer_ptrs, int world, int64_t peer_ld, int row0, int batch, int rows_per_batch,
+                                   void* stream);
 
 /* ---- self-attention ------------------------------------------------------------------------------------------
  * o[s, h*128 + d] = softmax_j(q[s,h,:]·k[j,h,:] / sqrt(128)) v[j,h,d]; no mask, no dropout, head_dim 128.
@@ -76,12 +86,30 @@ int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W, int64_t ld
  * `kv_len` keys/values, `q_len` queries (equal for the single-GPU path; they differ under context parallelism). */
 int drb_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                        int q_len, int kv_len, int num_heads, void* stream);
+/* The same with a caller-supplied certificate: *max_abs_logit is a DEVICE float B with |q.k| / sqrt(128) <= B (natural
+ * units) for every query / key pair (read by the kernel, so choosing the flavour costs no host synchronisation).  For
+ * B <= 39 the max-free lazy softmax runs (no per-element max; provably overflow-free under the bound whatever the key
+ * order); above it, or with NULL (= drb_attention_bf16), the per-tile-max softmax runs, which is exact for unbounded
+ * logits.  drb_qk_logit_bound computes B for q / k that went through the DiT's per-head RMSNorm. */
+int drb_attention_bf16_bounded(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                               int q_len, int kv_len, int num_heads, const float* max_abs_logit, void* stream);
+/* bound[l] = sqrt(128) * max|wq[l,:]| * max|wk[l,:]| * 1.02 for `layers` pairs of per-head RMSNorm weights wq, wk
+ * [layers,128] (bf16): after x -> rmsnorm(x) * w every head row has norm <= sqrt(128) max|w| (RoPE is a rotation; 1.02
+ * covers the bf16 roundings), so |q.k| / sqrt(128) <= bound (Cauchy-Schwarz).  CleanGeneralDIT.py:23-33,:288-297. */
+int drb_qk_logit_bound(const void* wq, const void* wk, float* bound, int layers, void* stream);
 
 /* Context-parallel form (csrc/cp.cu): the same kernel over the H/P heads this GPU owns and all tokens;
  * output row r is stored into o_peers[r / rows_per_rank] (a peer-mapped [rows_per_rank, ld_o] buffer of the GPU that
  * owns token r) at local row r % rows_per_rank, column col0 + h*128 — the inverse Ulysses exchange is the epilogue. */
 int drb_attention_bf16_cp(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
                           int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0, void* stream);
+/* Batched sequences (see drb_gemm_qkv_norm_rope_batched): num_heads = batch * heads_per_batch attention problems over the
+ * same token range; "head" g = b*heads_per_batch + h reads column g*128 of q / k / v and its output row r is stored at
+ * local row b*batch_rows + (r mod rows_per_rank), column col0 + h*128, of the owner's [batch*batch_rows, ld_o] buffer.
+ * max_abs_logit: as drb_attention_bf16_bounded. */
+int drb_attention_bf16_cp_batched(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
+                                  int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0,
+                                  int heads_per_batch, int batch_rows, const float* max_abs_logit, void* stream);
 
 /* ---- fused elementwise family ----------------------------------------------------------------------------------
  * AdaLN: out = bf16(bf16(bf16(LN(x)) * bf16(1+scale)) + shift), LN over `D` without affine, eps 1e-6, fp32 stats

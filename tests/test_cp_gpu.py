@@ -139,6 +139,56 @@ def test_emulated_ranks_are_bit_identical_to_one_gpu(dims, mt, world):
     assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_emulated_ranks_with_batched_passes_are_bit_identical_to_one_gpu(world):
+    """B = 3 sequences (G-buffer passes with different context vectors) stacked along the token rows of every rank: the fused
+    QKV epilogue scatters (sequence, head) pairs, the attention runs B*H/P problems per rank and scatters rows back.  S/P = 96
+    or 48 rows per sequence: 128-row GEMM tiles and 32-row epilogue warps straddle sequence boundaries."""
+    from drb200 import ops
+    from drb200.context_parallel import EmulatedGroup, shard_frames
+    dims = TINY_INVERSE
+    model, _ = build_product_model(dims, "inverse", seed=3)
+    net = model.net
+    T, H, W, B = 4, 12, 16, 3                             # S = 192 tokens per sequence
+    g = torch.Generator(device=DEV).manual_seed(5)
+    xs = torch.randn(B, 16, T, H, W, device=DEV, generator=g).bfloat16()
+    cond = (torch.randn(1, 16, T, H, W, device=DEV, generator=g) * 0.5).bfloat16()
+    cis = [torch.full((1, 1), k, dtype=torch.long, device=DEV) for k in (1, 4, 2)]
+    sigma = torch.tensor(1.26, device=DEV)
+    with torch.no_grad():
+        refs = [net(x=xs[b:b + 1], timesteps=sigma, latent_condition=cond, context_index=cis[b]) for b in range(B)]
+        group = EmulatedGroup(world)
+        wss = []
+        for cp in group.ranks:
+            t0, t1 = shard_frames(T, cp.rank, world)
+            ws = net._workspace(t1 - t0, H, W, xs.device, cp, batch=B)
+            ws["sigma"].copy_(sigma.reshape(1))
+            net.modulation(ws, ws["sigma"])
+            for b in range(B):
+                net.prepare_condition(ws, cond[:, :, t0:t1], t1 - t0, H, W, b)
+                ops.patchify_condition(xs[b, :, t0:t1].contiguous(), net._rows(ws, "tok", b), 0, t1 - t0, H, W)
+                use_ca = net.prepare_context(ws, net.context_token(cis[b]), b)
+            net.stage_embed(ws)
+            wss.append(ws)
+        for i in range(net.num_blocks):
+            for ws in wss:
+                net.stage_pre_attention(ws, i)
+            for ws in wss:
+                net.stage_attention(ws, i)
+            for ws in wss:
+                net.stage_post_attention(ws, i, use_ca)
+        outs = [[None] * world for _ in range(B)]
+        for cp, ws in zip(group.ranks, wss):
+            t0, t1 = shard_frames(T, cp.rank, world)
+            y = net.stage_final(ws)
+            for b in range(B):
+                out = torch.empty((16, t1 - t0, H, W), device=DEV, dtype=torch.bfloat16)
+                ops.unpatchify_euler(y[b * ws["S"]:(b + 1) * ws["S"]], None, 0.0, None, None, None, None, f_out=out)
+                outs[b][cp.rank] = out
+    for b in range(B):
+        assert torch.equal(torch.cat(outs[b], dim=1).unsqueeze(0), refs[b]), f"sequence {b}"
+
+
 def test_cp_rejects_uneven_splits():
     from drb200.context_parallel import EmulatedGroup
     model, _ = build_product_model(TINY_INVERSE, "inverse", seed=3)

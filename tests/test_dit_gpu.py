@@ -115,3 +115,27 @@ def test_public_scheduler_methods_match_oracle():
         ref = so.euler_step(f, t, s.sigmas[i + 1], x)
         assert (got.float() - ref.float()).abs().max() <= 2 ** -7 * ref.float().abs().max()
         assert (got == ref).float().mean() > 0.98
+
+
+def test_batched_passes_and_batched_cfg_are_bit_identical_to_sequential_sampling():
+    """sample_latent with a LIST of condition dicts runs the passes (and cond / uncond under CFG) as one
+    batched transformer pass per step; every row is computed exactly as in the one-pass-at-a-time loop of the reference
+    (model_diffusion_renderer.py:224-234), so the latents must be bit-identical."""
+    from oracle.weights import TINY_INVERSE
+    from tests.util import build_product_model
+    model, _ = build_product_model(TINY_INVERSE, "inverse", seed=3)
+    T, H, W = 3, 12, 20
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cond = (torch.randn(1, 16, T, H, W, device="cuda", generator=g) * 0.5).bfloat16()
+    conds = [{"latent_condition": cond, "context_index": torch.full((1, 1), k, dtype=torch.long, device="cuda")} for k in range(5)]
+    unconds = [{"latent_condition": torch.zeros_like(cond), "context_index": torch.zeros(1, 1, dtype=torch.long, device="cuda")}
+               for _ in conds]
+    with torch.no_grad():
+        model.scheduler.set_timesteps(4, device="cuda")
+        xt = torch.randn(1, 16, T, H, W, device="cuda", generator=g).bfloat16() * model.scheduler.sigmas[0]
+        seq = torch.cat([model.sample_latent(xt, c, None) for c in conds])
+        assert torch.equal(model.sample_latent(xt, conds, None), seq)
+        assert not torch.equal(seq[0], seq[3])                       # the passes do differ (context vectors)
+        seq_g = torch.cat([model.sample_latent(xt, c, u, guidance=2.0) for c, u in zip(conds, unconds)])
+        assert torch.equal(model.sample_latent(xt, conds, unconds, guidance=2.0), seq_g)
+        assert not torch.equal(seq_g, seq)

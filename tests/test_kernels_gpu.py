@@ -78,38 +78,108 @@ def test_gemm_rejects_bad_arguments():
         ops.gemm(a.float(), w)
     with pytest.raises(ValueError):
         ops.gemm(a.cpu(), w.cpu())
+    a8 = torch.zeros(16, 16, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.gemm(a8, a8, epilogue=3)                                  # the QKV epilogue is internal to drb_gemm_qkv_norm_rope
 
 
-@pytest.mark.parametrize("S,Skv,H", [(128, 128, 1), (512, 512, 4), (48, 48, 2), (1000, 1000, 2), (300, 700, 3), (4096, 4096, 2)])
-def test_attention(S, Skv, H):
+def _sdpa_ref(q, k, v, H, dtype=torch.float32):
+    S, Skv = q.shape[0], k.shape[0]
+    q4 = q.to(dtype).reshape(S, H, 128).permute(1, 0, 2)[None]
+    k4 = k.to(dtype).reshape(Skv, H, 128).permute(1, 0, 2)[None]
+    v4 = v.to(dtype).reshape(Skv, H, 128).permute(1, 0, 2)[None]
+    return F.scaled_dot_product_attention(q4, k4, v4)[0].permute(1, 0, 2).reshape(S, H * 128)
+
+
+def _max_abs_logit(q, k, H):
+    S, Skv = q.shape[0], k.shape[0]
+    qh = q.float().reshape(S, H, 128).permute(1, 0, 2)
+    kh = k.float().reshape(Skv, H, 128).permute(1, 0, 2)
+    return (qh @ kh.transpose(1, 2)).abs().max().item() / 128 ** 0.5
+
+
+@pytest.mark.parametrize("certified", [False, True], ids=["safe", "certified"])
+@pytest.mark.parametrize("S,Skv,H", [(128, 128, 1), (512, 512, 4), (48, 48, 2), (1000, 1000, 2), (300, 700, 3), (4096, 4096, 2),
+                                     (512, 1000, 2)])   # the last: K/V multicast pair (two query blocks) with a ragged key tile
+def test_attention(S, Skv, H, certified):
+    """both softmax flavours: the per-tile-max one (no certificate) and the max-free one under a logit bound"""
     from drb200 import ops
     g = gen(3)
     qkv = torch.randn(max(S, Skv), 3 * H * 128, device=DEV, generator=g).bfloat16()
     q, k, v = qkv[:S, :H * 128], qkv[:Skv, H * 128:2 * H * 128], qkv[:Skv, 2 * H * 128:]
-    out = ops.attention(q, k, v, H)
-    q4 = q.float().reshape(S, H, 128).permute(1, 0, 2)[None]
-    k4 = k.float().reshape(Skv, H, 128).permute(1, 0, 2)[None]
-    v4 = v.float().reshape(Skv, H, 128).permute(1, 0, 2)[None]
-    ref = F.scaled_dot_product_attention(q4, k4, v4)[0].permute(1, 0, 2).reshape(S, H * 128)
-    assert rel_l2(out, ref) <= 5e-3
+    bound = None
+    if certified:
+        assert _max_abs_logit(q, k, H) <= 39.0
+        bound = torch.tensor([39.0], device=DEV)
+    out = ops.attention(q, k, v, H, max_abs_logit=bound)
+    assert rel_l2(out, _sdpa_ref(q, k, v, H)) <= 5e-3
     # against the reference's own bf16 SDPA call (CleanGeneralDIT.py:192-197)
-    ref16 = F.scaled_dot_product_attention(q4.bfloat16(), k4.bfloat16(), v4.bfloat16())[0].permute(1, 0, 2).reshape(S, H * 128)
-    assert rel_l2(out, ref16) <= 8e-3
+    assert rel_l2(out, _sdpa_ref(q, k, v, H, torch.bfloat16)) <= 8e-3
 
 
-def test_attention_large_logits_rescale_path():
-    """row maxima that keep growing along kv force the lazy O-rescale branch"""
+@pytest.mark.parametrize("certified", [False, True], ids=["safe", "certified"])
+def test_attention_large_logits_rescale_path(certified):
+    """row maxima that keep growing along kv force the O-rescale branch of either flavour"""
     from drb200 import ops
     g = gen(4)
     S, H = 1024, 1
-    q = torch.randn(S, 128, device=DEV, generator=g).bfloat16() * 4
+    qs, k1 = (2.0, 3.0) if certified else (4.0, 6.0)
+    q = torch.randn(S, 128, device=DEV, generator=g).bfloat16() * qs
     k = torch.randn(S, 128, device=DEV, generator=g).bfloat16()
-    k = (k * torch.linspace(0.2, 6.0, S, device=DEV)[:, None]).bfloat16()      # later keys -> larger |logits|
+    k = (k * torch.linspace(0.2, k1, S, device=DEV)[:, None]).bfloat16()      # later keys -> larger |logits|
     v = torch.randn(S, 128, device=DEV, generator=g).bfloat16()
-    out = ops.attention(q, k, v, H)
-    ref = F.scaled_dot_product_attention(q.float()[None, None], k.float()[None, None], v.float()[None, None])[0, 0]
+    bound = None
+    if certified:
+        m = _max_abs_logit(q, k, H)
+        assert 12.0 <= m <= 39.0, m          # far above tile 0's maximum (the reference must move), inside the certificate
+        bound = torch.tensor([m], device=DEV)
+    out = ops.attention(q, k, v, H, max_abs_logit=bound)
     assert torch.isfinite(out.float()).all()
-    assert rel_l2(out, ref) <= 8e-3
+    assert rel_l2(out, _sdpa_ref(q, k, v, H)) <= 8e-3
+
+
+@pytest.mark.parametrize("Sq,Skv,where", [(1024, 1024, 700), (512, 1000, 999), (300, 4096, 2500)])
+def test_attention_sudden_outlier_logit(Sq, Skv, where):
+    """One key deep in the sequence scores ~100 natural units above everything before it (2^144 in the log2 domain: a
+    max-free softmax anchored at tile 0 would overflow).  Without a certificate the per-tile-max softmax must stay exact."""
+    from drb200 import ops
+    g = gen(11)
+    H = 2
+    q = (torch.randn(Sq, H * 128, device=DEV, generator=g) + 3.0).bfloat16()
+    k = torch.randn(Skv, H * 128, device=DEV, generator=g).bfloat16()
+    k[where] = 3.0                                                         # q.k / sqrt(128) ~ 128*3*3/11.3 = 102
+    v = torch.randn(Skv, H * 128, device=DEV, generator=g).bfloat16()
+    logits = (q.float()[:, :128] @ k.float()[:, :128].t()) / 128 ** 0.5
+    assert (logits[:, where] - logits[:, :where].max(dim=1).values).min().item() > 60.0
+    out = ops.attention(q, k, v, H)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, _sdpa_ref(q, k, v, H)) <= 8e-3
+    # a certificate that the data violates must not be honoured blindly when it is above the kernel's limit
+    out2 = ops.attention(q, k, v, H, max_abs_logit=torch.tensor([150.0], device=DEV))
+    assert torch.equal(out, out2)
+
+
+def test_qk_logit_bound_certifies_normed_heads():
+    """drb_qk_logit_bound >= the largest |q.k|/sqrt(128) the per-head RMSNorm + RoPE can produce with these weights"""
+    from drb200 import ops
+    g = gen(12)
+    L, S = 3, 256
+    wq = (1.0 + 0.3 * torch.randn(L, 128, device=DEV, generator=g)).bfloat16()
+    wk = (1.0 + 0.3 * torch.randn(L, 128, device=DEV, generator=g)).bfloat16()
+    b = ops.qk_logit_bound(wq, wk)
+    want = 128 ** 0.5 * wq.float().abs().amax(1) * wk.float().abs().amax(1) * 1.02
+    assert torch.allclose(b, want, rtol=1e-5)
+    ang = torch.rand(S, 128, device=DEV, generator=g) * 6.28
+    cos, sin = ang.cos().bfloat16(), ang.sin().bfloat16()
+    for l in range(L):
+        # adversarial rows: all the energy of a head in the dimension with the largest weight
+        qkv = torch.randn(S, 3 * 128, device=DEV, generator=g).bfloat16() * 0.01
+        qkv[:, wq[l].float().abs().argmax()] = 50.0
+        qkv[:, 128 + wk[l].float().abs().argmax()] = 50.0
+        ops.qk_norm_rope(qkv, wq[l], wk[l], cos, sin, 1)
+        assert _max_abs_logit(qkv[:, :128], qkv[:, 128:256], 1) <= b[l].item()
+    wq[1, 5] = float("nan")
+    assert torch.isinf(ops.qk_logit_bound(wq, wk)[1])
 
 
 @pytest.mark.parametrize("D", [256, 512, 4096])
