@@ -31,7 +31,8 @@ Keys beyond the base contract:
   gpu_baseline the "existing Blackwell path": the reference's operator sequence through stock PyTorch (cuBLASLt, SDPA,
                unfused elementwise) for one block on the same GPU, run back to back for >= 3 s, x28 (N = 1 only).
   step_tflops  whole-step achieved TFLOP/s (6.8132e14 algorithmic FLOP per step) and its fraction of the peak.
-  host_enqueue_ms_per_step   host time to enqueue one step's launches (no CUDA graph: the host runs far ahead).
+  host_enqueue_ms_per_iteration   host time to enqueue one iteration's launches into an empty stream (ctypes calls + tensor-map
+               encoding; no CUDA graph) — compare with ms_per_iteration: the host runs far ahead of the GPU.
   video        seconds per inverse-rendered video measured through the pipeline API (host fp32 clip in, host uint8
                frames out): N = 1 generate_video x 5 passes; N > 1 generate_video_passes (one batched sampler run).
 `--impl reference` times the reference's own CPU implementation of the path (the oracle port, all host threads).
@@ -411,15 +412,20 @@ def timed_steps(torch, dist, world, local, net, ws, xs, sig, use_ca, steps, warm
     launches0 = _lib.LAUNCHES
     with ClockSampler(local) as clk:
         e0.record()
-        h0 = time.perf_counter()
         for i in range(steps):
             step(warmup + i, timers)
-        host_ms = (time.perf_counter() - h0) * 1e3
         e1.record()
         sync()
+    launched = _lib.LAUNCHES - launches0
+    # host cost of enqueueing ONE iteration into an empty stream (inside the timed region the host runs ahead until the
+    # driver's launch queue is full and then blocks on the GPU, which says nothing about the enqueue cost itself)
+    h0 = time.perf_counter()
+    step(warmup + steps)
+    host_ms = (time.perf_counter() - h0) * 1e3
+    sync()
     if not torch.isfinite(xs.float()).all():
         raise SystemExit("non-finite latent after the timed steps")
-    return e0.elapsed_time(e1), host_ms, _lib.LAUNCHES - launches0, clk.summary()
+    return e0.elapsed_time(e1), host_ms, launched, clk.summary()
 
 
 def run_b200(args, wl):
@@ -439,7 +445,10 @@ def run_b200(args, wl):
         mode = "single" if world == 1 else ("cp" if wl["H"] % world == 0 and t % world == 0 else "dp")
     if world == 1:
         mode = "single"
-    batch = args.cp_batch if mode == "cp" else 1
+    # passes batched per iteration: 5 (all G-buffer passes of the video) from 4 GPUs up, where M = S/N rows per pass would
+    # leave the GEMM grids with a short last wave; 1 at N = 2 (full waves anyway, and alternating attention / GEMM phases
+    # run ~3 % faster under the power cap than long homogeneous phases: profiles/r02_cp2_batch_and_sync_sweep.log)
+    batch = (args.cp_batch or (5 if world >= 4 else 1)) if mode == "cp" else 1
 
     cp, gate = None, None
     if mode in ("cp", "ring"):
@@ -481,6 +490,8 @@ def run_b200(args, wl):
     ws, xs, use_ca = setup(cp, batch, 0 if cp is not None else rank)
     timers = []
     ms, host_ms, launches, clocks = timed_steps(torch, dist, world, local, net, ws, xs, sig, use_ca, args.steps, args.warmup, timers)
+    if cp is not None:
+        cp.check()      # no in-kernel wait for a peer timed out
     attn_ms = statistics.mean(a.elapsed_time(b) for a, b in timers)
 
     # ---- e2e: the public call with pinned host buffers (H2D + D2H inside the timed region)
@@ -597,7 +608,7 @@ def run_b200(args, wl):
                          "share_of_step": attn_ms * wl["L"] / (ms / args.steps)},
             "step_tflops": {"achieved_per_gpu": step_tf, "flops_per_step": F, "frac_of_sustained_peak": step_tf / peak,
                             "frac_of_burst_peak": step_tf / pk["bf16_tflops"]},
-            "host_enqueue_ms_per_step": host_max / args.steps / (batch if mode == "cp" else 1),
+            "host_enqueue_ms_per_iteration": host_max,
             # one inverse video = 5 G-buffer passes x 15 steps (DiT only; the measured end-to-end figure is `video`)
             "s_per_video_dit_only": 5 * 15 / steps_per_s if mode != "dp" else -(-5 // world) * 15 / (steps_per_s / world),
             "clocks": clocks,
@@ -702,7 +713,7 @@ def main():
     ap.add_argument("--no-video", action="store_true", help="skip the measured end-to-end video leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch block on the same GPU (N = 1)")
     ap.add_argument("--no-dp-leg", action="store_true", help="N > 1: skip the extra data-parallel measurement")
-    ap.add_argument("--cp-batch", type=int, default=5, help="G-buffer passes batched per context-parallel iteration")
+    ap.add_argument("--cp-batch", type=int, default=0, help="G-buffer passes batched per context-parallel iteration (0 = auto)")
     ap.add_argument("--parallel", default="auto", choices=["auto", "dp", "cp", "ring"],
                     help="N > 1: auto = cp when N divides the heads and the latent frames; cp = one video split over the GPUs "
                          "(Ulysses exchange fused into the kernels, passes batched); dp = one independent pass per GPU (weak "

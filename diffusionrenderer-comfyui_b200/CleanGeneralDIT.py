@@ -267,8 +267,8 @@ class CleanGeneralDIT(nn.Module):
         new = lambda *s, dtype=BF16: torch.empty(*s, device=dev, dtype=dtype)
         kpad = self._packed["wx"].shape[1]
         world, rank = (cp.world, cp.rank) if cp is not None else (1, 0)
-        if batch > 1 and cp is not None and (cp.mode == "ring" or S < 32):
-            raise ValueError("batched sequences under context parallelism need the Ulysses mode and >= 32 local tokens")
+        if batch > 1 and cp is not None and cp.mode != "ring" and S < 32:
+            raise ValueError("batched sequences under context parallelism need >= 32 local tokens per sequence")
         cos, sin = self.pos_embedder.tables(T * world, H // 2, W // 2, BF16)
         cos, sin = cos[rank * S:(rank + 1) * S].repeat(batch, 1).contiguous(), sin[rank * S:(rank + 1) * S].repeat(batch, 1).contiguous()
         ws = {
@@ -283,8 +283,8 @@ class CleanGeneralDIT(nn.Module):
         elif cp.mode == "ring":
             # every rank's [q | k | v] rows are visible to the others; remote K/V blocks land in two staging buffers of the
             # same row pitch (only their k | v columns are written); fp32 running softmax state of the local query rows
-            ws["attn"] = new(S, D)
-            ws["qkv"], ws["qkv_peers"] = cp.alloc_views("qkv", (S, 3 * D))
+            ws["attn"] = new(R, D)
+            ws["qkv"], ws["qkv_peers"] = cp.alloc_views("qkv", (R, 3 * D))
             ws["kv_stage"] = [new(S, 3 * D), new(S, 3 * D)]
             ws["ring_o"] = new(S, D, dtype=torch.float32)
             ws["ring_ml"] = new(S, self.num_heads, 2, dtype=torch.float32)
@@ -338,14 +338,14 @@ class CleanGeneralDIT(nn.Module):
     def stage_embed(self, ws) -> None:
         ops.gemm(ws["tok"], self._packed["wx"], out=ws["x"])
 
-    def stage_pre_attention(self, ws, i: int) -> None:
+    def stage_pre_attention(self, ws, i: int, sync=None) -> None:
         """AdaLN -> fused QKV GEMM whose epilogue does the per-head RMSNorm + RoPE of q and k (under context parallelism
         it also stores every head's rows straight into the GPU that owns the head: the all-to-all is the epilogue)"""
         P, D, cp, B = self._packed, self.model_channels, ws["cp"], ws["B"]
         m_sa = ws["mod"][3 * i]
         ops.adaln_modulate(ws["x"], m_sa[:D], m_sa[D:2 * D], out=ws["xm"])
         if not self.fuse_qkv_epilogue:
-            if B > 1 and cp is not None:
+            if B > 1 and cp is not None and cp.mode != "ring":
                 raise ValueError("the stand-alone scatter kernel (A/B reference) handles one sequence; use fuse_qkv_epilogue")
             qkv = ws.get("qkv")
             if qkv is None:
@@ -360,9 +360,9 @@ class CleanGeneralDIT(nn.Module):
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], out=ws["qkv"])
         else:
             ops.qkv_gemm_norm_rope(ws["xm"], P["qkv"][i], P["qn"][i], P["kn"][i], ws["cos"], ws["sin"], peer_ptrs=ws["a2a_ptrs"],
-                                   peer_ld=3 * B * D // cp.world, row0=cp.rank * ws["S"], batch=B)
+                                   peer_ld=3 * B * D // cp.world, row0=cp.rank * ws["S"], batch=B, sync=sync)
 
-    def stage_attention(self, ws, i: int, timers: Optional[list] = None) -> None:
+    def stage_attention(self, ws, i: int, timers: Optional[list] = None, sync=None) -> None:
         D, Hh, cp, B, S = self.model_channels, self.num_heads, ws["cp"], ws["B"], ws["S"]
         bound = ws["qk_bound"][i:i + 1]
         if timers is not None:
@@ -373,25 +373,27 @@ class CleanGeneralDIT(nn.Module):
                 qkv = ws["qkv"][b * S:(b + 1) * S]
                 ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Hh, out=ws["attn"][b * S:(b + 1) * S], max_abs_logit=bound)
         elif cp.mode == "ring":
-            self._ring_attention(ws)
+            for b in range(B):          # the ring schedule runs per sequence (staging buffers and running state are reused)
+                self._ring_attention(ws, b)
         else:
             # (sequence, local head) pairs are the attention problems of this rank: B * H/P "heads" over all S tokens
             Hp, a2a = Hh // cp.world, ws["a2a"]
             w = B * Hp * 128
             ops.attention_cp(a2a[:, :w], a2a[:, w:2 * w], a2a[:, 2 * w:], B * Hp, ws["attn_ptrs"], D, S, cp.rank * Hp * 128,
-                             heads_per_batch=Hp, batch_rows=S, max_abs_logit=bound)
+                             heads_per_batch=Hp, batch_rows=S, max_abs_logit=bound, sync=sync)
         if timers is not None:
             ev[1].record()
             timers.append(ev)
 
-    def _ring_attention(self, ws) -> None:
-        """Ring schedule over peer memory: block s of rank r is the K/V of rank (r - s) mod P.  While block s is attended
-        to on the current stream, block s + 1 is pulled from its owner's [q | k | v] buffer (k | v columns only) into the
-        other staging buffer on the copy stream; the attention kernel's ring epilogue merges the blocks."""
-        D, Hh, cp = self.model_channels, self.num_heads, ws["cp"]
+    def _ring_attention(self, ws, b: int = 0) -> None:
+        """Ring schedule over peer memory for sequence b: block s of rank r is the K/V of rank (r - s) mod P.  While block s
+        is attended to on the current stream, block s + 1 is pulled from its owner's [q | k | v] buffer (k | v columns only)
+        into the other staging buffer on the copy stream; the attention kernel's ring epilogue merges the blocks."""
+        D, Hh, cp, S = self.model_channels, self.num_heads, ws["cp"], ws["S"]
         P, r = cp.world, cp.rank
+        rows = slice(b * S, (b + 1) * S)
         main, side = torch.cuda.current_stream(), cp.copy_stream
-        q = ws["qkv"][:, :D]
+        q = ws["qkv"][rows, :D]
         ready = torch.cuda.Event()
         ready.record(main)                    # the barrier before this stage: every rank's K/V rows are in place
         side.wait_event(ready)
@@ -402,23 +404,23 @@ class CleanGeneralDIT(nn.Module):
                 if (s - 1) in freed:          # the attention that read this staging buffer two steps ago must be done
                     side.wait_event(freed[s - 1])
                 with torch.cuda.stream(side):
-                    nxt[:, D:].copy_(ws["qkv_peers"][(r - s - 1) % P][:, D:], non_blocking=True)
+                    nxt[:, D:].copy_(ws["qkv_peers"][(r - s - 1) % P][rows, D:], non_blocking=True)
                     copied[s + 1] = torch.cuda.Event()
                     copied[s + 1].record(side)
-            kv = ws["qkv"] if s == 0 else ws["kv_stage"][s & 1]
+            kv = ws["qkv"][rows] if s == 0 else ws["kv_stage"][s & 1]
             if s > 0:
                 main.wait_event(copied[s])
             ops.attention_ring_block(q, kv[:, D:2 * D], kv[:, 2 * D:], Hh, ws["ring_o"], ws["ring_ml"], first=(s == 0),
-                                     last=(s == P - 1), out=ws["attn"])
+                                     last=(s == P - 1), out=ws["attn"][rows])
             freed[s] = torch.cuda.Event()
             freed[s].record(main)
 
-    def stage_post_attention(self, ws, i: int, use_ca: bool) -> None:
+    def stage_post_attention(self, ws, i: int, use_ca: bool, sync=None) -> None:
         """out-projection with gated residual; cross-attention vector + AdaLN; MLP with gated residual"""
         P, D, B, S = self._packed, self.model_channels, ws["B"], ws["S"]
         x, xm, h, mod = ws["x"], ws["xm"], ws["h"], ws["mod"]
         m_sa, m_ca, m_mlp = mod[3 * i], mod[3 * i + 1], mod[3 * i + 2]
-        ops.gemm(ws["attn"], P["wo"][i], out=x, epilogue=_lib.EPI_GATED_RESIDUAL, resid=x, gate=m_sa[2 * D:])
+        ops.gemm(ws["attn"], P["wo"][i], out=x, epilogue=_lib.EPI_GATED_RESIDUAL, resid=x, gate=m_sa[2 * D:], sync=sync)
         if use_ca:      # the cross-attention vector is the only per-sequence term of a block
             for b in range(B):
                 ops.adaln_modulate(x[b * S:(b + 1) * S], m_mlp[:D], m_mlp[D:2 * D], out=xm[b * S:(b + 1) * S],
@@ -438,11 +440,20 @@ class CleanGeneralDIT(nn.Module):
     def run_blocks(self, ws, use_ca: bool, timers: Optional[list] = None) -> torch.Tensor:
         """tokens -> y [B*S, 64].  Consumes ws['tok'] / ws['mod'] / ws['ca_vec'].
         `timers` (bench only): a list that receives one (start, end) CUDA-event pair per attention stage.
-        Under context parallelism the two device-side barriers per block order the P2P stores of the fused exchange:
-        q/k/v rows must have landed before the attention reads them, its output rows before the out-projection."""
+        Under context parallelism the P2P stores of the fused exchange are ordered twice per block: q / k / v rows must have
+        landed before the attention reads them, its output rows before the out-projection.  With `cp.fused_sync` that is a
+        flag published by the producer kernel's last CTA and awaited by the consumer kernel's TMA-producer thread (no launch
+        in between); otherwise a stand-alone device barrier kernel."""
         cp = ws["cp"]
+        fused = cp is not None and getattr(cp, "fused_sync", False) and cp.mode == "ulysses" and self.fuse_qkv_epilogue
         self.stage_embed(ws)
         for i in range(self.num_blocks):
+            if fused:
+                e_q, e_a = cp.next_epoch(_lib.CP_SLOT_QKV), cp.next_epoch(_lib.CP_SLOT_ATTN)
+                self.stage_pre_attention(ws, i, sync=cp.sync(signal=(_lib.CP_SLOT_QKV, e_q)))
+                self.stage_attention(ws, i, timers, sync=cp.sync(wait=(_lib.CP_SLOT_QKV, e_q), signal=(_lib.CP_SLOT_ATTN, e_a)))
+                self.stage_post_attention(ws, i, use_ca, sync=cp.sync(wait=(_lib.CP_SLOT_ATTN, e_a)))
+                continue
             self.stage_pre_attention(ws, i)
             if cp is not None:
                 cp.barrier()

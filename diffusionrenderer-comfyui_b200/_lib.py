@@ -23,10 +23,18 @@ class Conv3dArgs(Structure):
                     "stride_hw", "tmode", "out_scale", "out_off_h", "out_off_w", "resid_mode", "resid_H", "resid_W")]
 
 
+class CpSync(Structure):
+    """drb_cp_sync of include/drb200.h"""
+    _fields_ = [("flag_ptrs", POINTER(c_void_p)), ("counter", c_void_p), ("world", c_int), ("rank", c_int), ("signal_slot", c_int),
+                ("wait_slot", c_int), ("signal_epoch", c_uint32), ("wait_epoch", c_uint32), ("timeout_ms", c_uint32)]
+
+
 # name -> argtypes, in the order of include/drb200.h (tests check that every one is exported)
 PROTOTYPES = {
     "drb_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
                       c_int64, c_void_p, c_int, c_void_p],
+    "drb_gemm_bf16_sync": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
+                           c_int64, c_void_p, c_int, POINTER(CpSync), c_void_p],
     "drb_attention_bf16": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     "drb_adaln_modulate": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "drb_qk_norm_rope": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
@@ -59,11 +67,11 @@ PROTOTYPES = {
     "drb_gemm_qkv_norm_rope": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, POINTER(c_void_p), c_int, c_int64, c_int, c_void_p],
     "drb_gemm_qkv_norm_rope_batched": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int, c_void_p],
+                                       c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int, POINTER(CpSync), c_void_p],
     "drb_attention_bf16_bounded": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p],
     "drb_qk_logit_bound": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "drb_attention_bf16_cp_batched": [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int,
-                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+                                      c_int, c_int, c_int, c_int, c_void_p, POINTER(CpSync), c_void_p],
     "drb_attention_bf16_cp": [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int, c_int,
                               c_int, c_void_p],
     "drb_cp_qk_norm_rope_scatter": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p), c_int,
@@ -76,6 +84,8 @@ PROTOTYPES = {
     "drb_peer_close": [c_void_p],
 }
 CP_MAX_RANKS = 8
+CP_FLAG_SLOTS, CP_STATUS_WORD = 4, 63
+CP_SLOT_BARRIER, CP_SLOT_QKV, CP_SLOT_ATTN = 0, 1, 2   # flag slots: stand-alone barrier, "q/k/v stored", "attention rows stored"
 PEER_HANDLE_BYTES = 64
 
 

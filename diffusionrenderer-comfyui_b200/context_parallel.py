@@ -4,8 +4,14 @@ Tokens are split contiguously along the latent time axis over P ranks (one proce
 GeneralDIT is token-local except self-attention; the Ulysses exchange around it (tokens-sharded <-> heads-sharded) is
 fused into the producing kernels as P2P stores over NVLink into peer-mapped buffers:
 
-    qk_norm_rope_scatter  ->  [device barrier]  ->  attention over H/P heads x all S tokens, epilogue stores each output
-    row to the GPU that owns the token  ->  [device barrier]  ->  out-projection on the local tokens
+    QKV GEMM whose epilogue normalises / rotates q, k and stores every head's rows into the GPU that owns the head
+      -> attention over H/P heads x all S tokens, epilogue stores each output row to the GPU that owns the token
+      -> out-projection on the local tokens
+
+The ordering between a producer's P2P stores and the consumer on another GPU is folded into the kernels themselves
+(`fused_sync`, csrc/cp_sync.cuh): the producer kernel's last CTA publishes a flag to every peer, the consumer kernel's
+TMA-producer thread waits for all ranks' flags right before its first operand load.  `barrier()` — one tiny stand-alone
+kernel between the stages — is the A/B reference of that and what the ring mode uses.
 
 Two exchange schemes share the plumbing (`mode`):
   "ulysses" (default)  heads are split for the attention; the exchange is fused into the QKV GEMM epilogue and the
@@ -105,6 +111,12 @@ class PeerBuffer:
         src = self.bytes_tensor if rank is None else self.peer_bytes[rank]
         return src[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self) -> None:
         lib = _lib.load()
         for p in self._imported:
@@ -131,8 +143,19 @@ class ContextParallel:
         if self.world > _lib.CP_MAX_RANKS:
             raise ValueError(f"at most {_lib.CP_MAX_RANKS} ranks")
         self._buffers: Dict[str, PeerBuffer] = {}
-        self._flags = PeerBuffer(256, group)
+        self._flags = PeerBuffer(256, group)       # uint32 [CP_FLAG_SLOTS][CP_MAX_RANKS] + status word, zeroed
+        self._flag_array = _lib.ptr_array(self._flags.ptrs)
+        self._counters = torch.zeros(_lib.CP_FLAG_SLOTS, dtype=torch.int32, device="cuda")   # per-slot CTA counters
+        self._epochs = [0] * _lib.CP_FLAG_SLOTS
         self._epoch = 0
+        # True: flag waits inside the kernels instead of barrier kernels between them.  Measured slower on B200 (cp8, five
+        # batched passes: 68.4 vs 67.2 ms per step; cp2: 268 vs 263): every attention CTA must fence its P2P stores at
+        # system scope before it may count itself done — a NVLink round trip at the tail of each of 2 200 CTAs that hold
+        # the whole SM — whereas the barrier kernel fences once per launch (profiles/r02_cp8_batch_and_sync_sweep.log).
+        self.fused_sync = False
+        self.timeout_ms = 60000
+        import weakref
+        self._finalizer = weakref.finalize(self, ContextParallel._release, self._buffers, self._flags)
 
     def alloc(self, name: str, shape, dtype=BF16) -> Tuple[torch.Tensor, List[int]]:
         """collective: every rank calls it with the same arguments in the same order"""
@@ -158,14 +181,45 @@ class ContextParallel:
         _lib.call("drb_cp_barrier", _lib.ptr_array(self._flags.ptrs), self.rank, self.world, self._epoch,
                   torch.cuda.current_stream().cuda_stream)
 
+    def next_epoch(self, slot: int) -> int:
+        """the next epoch of a flag slot (every rank calls this in the same order: SPMD)"""
+        self._epochs[slot] += 1
+        return self._epochs[slot]
+
+    def sync(self, signal=None, wait=None) -> "_lib.CpSync":
+        """drb_cp_sync descriptor for one kernel launch: `signal` / `wait` = (slot, epoch) or None"""
+        d = _lib.CpSync()
+        d.flag_ptrs = ctypes.cast(self._flag_array, ctypes.POINTER(ctypes.c_void_p))
+        d.world, d.rank, d.timeout_ms = self.world, self.rank, self.timeout_ms
+        d.counter = None
+        if signal is not None:
+            d.signal_slot, d.signal_epoch = signal
+            d.counter = self._counters.data_ptr() + 4 * signal[0]
+        if wait is not None:
+            d.wait_slot, d.wait_epoch = wait
+        return d
+
+    def check(self) -> None:
+        """Synchronises the device and raises if an in-kernel wait (or the barrier kernel) gave up on a peer."""
+        torch.cuda.synchronize()
+        status = self._flags.view((64,), torch.int32)[_lib.CP_STATUS_WORD]
+        if int(status.item()) != 0:
+            raise RuntimeError("context parallelism: a device-side wait for a peer GPU timed out (a rank died or fell "
+                               f"more than {self.timeout_ms / 1000:.0f} s behind); results since then are invalid")
+
     def all_gather_frames(self, x_local: torch.Tensor) -> torch.Tensor:
         return gather_frames(x_local, self.group)
 
-    def close(self) -> None:
-        for b in self._buffers.values():
+    @staticmethod
+    def _release(buffers, flags) -> None:
+        for b in buffers.values():
             b.close()
-        self._buffers = {}
-        self._flags.close()
+        buffers.clear()
+        flags.close()
+
+    def close(self) -> None:
+        """Frees the peer buffers and IPC mappings (also runs when the object is garbage-collected)."""
+        self._finalizer()
 
 
 class EmulatedGroup:
@@ -175,6 +229,7 @@ class EmulatedGroup:
 
     def __init__(self, world: int, mode: str = "ulysses"):
         self.world, self.mode = world, mode
+        self.fused_sync = False
         self._tensors: Dict[str, List[torch.Tensor]] = {}
         self.copy_stream = torch.cuda.Stream()
         self.ranks = [_EmulatedRank(self, r) for r in range(world)]
@@ -189,6 +244,7 @@ class EmulatedGroup:
 class _EmulatedRank:
     def __init__(self, group: EmulatedGroup, rank: int):
         self._g, self.rank, self.world, self.mode, self.copy_stream = group, rank, group.world, group.mode, group.copy_stream
+        self.fused_sync = False
 
     def alloc_views(self, name: str, shape, dtype=BF16):
         ts = self._g._alloc(name, shape, dtype)

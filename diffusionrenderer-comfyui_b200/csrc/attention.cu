@@ -24,6 +24,7 @@
 
 #include "../../include/drb200.h"
 #include "common.cuh"
+#include "cp_sync.cuh"
 #include "ptx.cuh"
 
 namespace drb {
@@ -57,6 +58,9 @@ struct AttnParams {
   // per-tile-max softmax, 0 by certificate, -1 never (tuning only)
   const float* logit_bound;
   int force_safe;
+  // context parallelism: wait for the peers' q / k / v stores before the first load, signal the peers once every CTA has
+  // stored its output rows (csrc/cp_sync.cuh); off unless a drb_cp_sync descriptor was passed
+  CpSync sync;
   // ring form (drb_attention_bf16_ring): this launch is one K/V block of a longer key sequence.  The running state per
   // (row, head) — reference m (log2 domain), sum l, un-normalised fp32 output — lives in ring_ml [q_len, H, 2] and ring_o
   // [q_len, H*128]; the epilogue merges this block into it and, on the last block, writes the normalised bf16 rows.
@@ -216,6 +220,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (warp_idx == 0 && lane == 0) {
       // ---------------------------------------------------------------- TMA producer
       const int col = head * kHeadDim;
+      cp_wait(p.sync);   // q / k / v rows stored by peer GPUs (the QKV GEMM epilogue's scatter) must have landed
       mbar_arrive_expect_tx(q_full, kQTilesPerCta * kTileBytes);
       for (int t = 0; t < kQTilesPerCta; ++t)
         for (int b = 0; b < 2; ++b)
@@ -543,6 +548,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
+    if (p.sync.signal_epoch != 0) {   // uniform: every output row of this CTA is stored -> count it; the last CTA tells the peers
+      __threadfence_system();
+      named_bar_sync(1, 256);
+      if (warp_idx == 4 && lane == 0) cp_signal_when_grid_done(p.sync, gridDim.x * gridDim.y);
+    }
   }
 
   __syncwarp();
@@ -566,6 +576,7 @@ struct AttnLaunchExtra {
   int ring_first = 0, ring_last = 0;
   int heads_per_batch = 0, batch_rows = 0;   // 0: unbatched
   const float* logit_bound = nullptr;        // the caller's certificate (device float); NULL = none (safe softmax)
+  const drb_cp_sync* sync = nullptr;
 };
 
 template <uint32_t kMask>
@@ -603,6 +614,10 @@ static int attention_launch(const void* q, const void* k, const void* v, int64_t
                   static_cast<int64_t>(rows_per_rank) * world >= q_len, "rows_per_rank * world must cover q_len");
   DRB_REQUIRE((reinterpret_cast<uintptr_t>(ex.logit_bound) & 3) == 0, "logit bound pointer misaligned");
   AttnParams p{};
+  {
+    const int rc_sync = fill_cp_sync(&p.sync, ex.sync);
+    if (rc_sync) return rc_sync;
+  }
   for (int i = 0; i < world; ++i) {
     DRB_REQUIRE(o_peers[i] != nullptr && (reinterpret_cast<uintptr_t>(o_peers[i]) & 15) == 0, "o not 16-byte aligned");
     p.o_peers[i] = o_peers[i];
@@ -682,17 +697,18 @@ extern "C" int drb_attention_bf16_cp(const void* q, const void* k, const void* v
                                      int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0,
                                      void* stream) {
   return drb_attention_bf16_cp_batched(q, k, v, ld_qkv, o_peers, world, ld_o, q_len, kv_len, num_heads, rows_per_rank, col0, num_heads,
-                                       0, nullptr, stream);
+                                       0, nullptr, nullptr, stream);
 }
 
 extern "C" int drb_attention_bf16_cp_batched(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers,
                                              int world, int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank,
                                              int col0, int heads_per_batch, int batch_rows, const float* max_abs_logit,
-                                             void* stream) {
+                                             const drb_cp_sync* sync, void* stream) {
   drb::AttnLaunchExtra ex;
   ex.heads_per_batch = heads_per_batch;
   ex.batch_rows = batch_rows;
   ex.logit_bound = max_abs_logit;
+  ex.sync = sync;
   return attention_launch(q, k, v, ld_qkv, o_peers, world, ld_o, q_len, kv_len, num_heads, rows_per_rank, col0, stream, ex);
 }
 

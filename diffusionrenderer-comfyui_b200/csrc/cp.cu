@@ -94,7 +94,12 @@ cp_barrier_kernel(const PeerPtrs flags, int rank, int world, uint32_t epoch) {
     uint32_t spins = 0;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > 20000000000ull) __trap();   // a lost peer: fail, do not hang
+      if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > 60000000000ull) {
+        // a lost peer: report through the local status word (the host checks it) and carry on — a trap would kill the
+        // CUDA context of the whole process
+        static_cast<uint32_t*>(flags.p[rank])[DRB_CP_STATUS_WORD] = 1u;
+        break;
+      }
     } while (static_cast<int32_t>(v - epoch) < 0);
   }
 }

@@ -20,6 +20,7 @@
 
 #include "../../include/drb200.h"
 #include "common.cuh"
+#include "cp_sync.cuh"
 #include "ptx.cuh"
 
 namespace drb {
@@ -68,6 +69,9 @@ struct GemmParams {
   // r / rows_per_batch; under context parallelism sequence b's heads occupy columns (b*heads_per_rank + h)*128 of each
   // section of the peer row, sections being `batch` times wider.  batch == 1: rows_per_batch = INT_MAX / 2.
   int rows_per_batch, batch;
+  // context parallelism: wait for the peers' stores into A before the first load / signal the peers once every CTA has
+  // stored its rows (csrc/cp_sync.cuh); both off unless a drb_cp_sync descriptor was passed
+  CpSync sync;
 };
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int band_n, int& m, int& n) {
@@ -139,6 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      cp_wait(p.sync);   // A rows stored by peer GPUs (the attention epilogue's scatter) must have landed
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int tm, tn;
         tile_coords(t, tiles_m, tiles_n, p.band, tm, tn);
@@ -394,6 +399,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
       }
     }
+    if (p.sync.signal_epoch != 0) {   // uniform: every row of this CTA is stored -> count it; the last CTA tells the peers
+      __threadfence_system();
+      named_bar_sync(1, 128);
+      if (warp_idx == 4 && lane == 0) cp_signal_when_grid_done(p.sync, gridDim.x);
+    }
   }
 
   // ------------------------------------------------------------------ teardown
@@ -472,6 +482,12 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 extern "C" int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M,
                              int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
                              int cta_group, void* stream) {
+  return drb_gemm_bf16_sync(A, lda, W, ldw, out, ldo, M, N, K, epilogue, resid, ldr, gate, cta_group, nullptr, stream);
+}
+
+extern "C" int drb_gemm_bf16_sync(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M,
+                                  int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
+                                  int cta_group, const drb_cp_sync* sync, void* stream) {
   using namespace drb;
   DRB_REQUIRE(A && W && out, "null pointer");
   DRB_REQUIRE(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
@@ -493,6 +509,8 @@ extern "C" int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, kBlockN / cta_group, kBlockK);
   if (rc) return rc;
   GemmParams p{};
+  rc = fill_cp_sync(&p.sync, sync);
+  if (rc) return rc;
   p.M = M; p.N = N; p.K = K;
   p.band = pick_band(K);
   {
@@ -516,13 +534,13 @@ extern "C" int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W,
                                       int K, const void* wq, const void* wk, const void* cos_tab, const void* sin_tab,
                                       void* const* peer_ptrs, int world, int64_t peer_ld, int row0, void* stream) {
   return drb_gemm_qkv_norm_rope_batched(A, lda, W, ldw, out, ldo, M, D, K, wq, wk, cos_tab, sin_tab, peer_ptrs, world, peer_ld, row0,
-                                        1, M, stream);
+                                        1, M, nullptr, stream);
 }
 
 extern "C" int drb_gemm_qkv_norm_rope_batched(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M,
                                               int D, int K, const void* wq, const void* wk, const void* cos_tab,
                                               const void* sin_tab, void* const* peer_ptrs, int world, int64_t peer_ld, int row0,
-                                              int batch, int rows_per_batch, void* stream) {
+                                              int batch, int rows_per_batch, const drb_cp_sync* sync, void* stream) {
   using namespace drb;
   DRB_REQUIRE(batch >= 1 && rows_per_batch >= 1 && static_cast<int64_t>(batch) * rows_per_batch == M,
               "batch * rows_per_batch must equal M");
@@ -533,6 +551,10 @@ extern "C" int drb_gemm_qkv_norm_rope_batched(const void* A, int64_t lda, const 
   DRB_REQUIRE(((reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk) | reinterpret_cast<uintptr_t>(cos_tab) |
                 reinterpret_cast<uintptr_t>(sin_tab)) & 15) == 0, "norm weights / RoPE tables must be 16-byte aligned");
   GemmParams p{};
+  {
+    const int rc_sync = fill_cp_sync(&p.sync, sync);
+    if (rc_sync) return rc_sync;
+  }
   p.M = M; p.N = 3 * D; p.K = K;
   p.band = pick_band(K);
   p.wq = static_cast<const __nv_bfloat16*>(wq);

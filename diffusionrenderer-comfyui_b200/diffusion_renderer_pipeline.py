@@ -54,6 +54,10 @@ class CleanDiffusionRendererPipeline:
         # on when the net is split over several GPUs (context parallelism), where batching removes the short GEMM waves
         self.batch_passes: Optional[bool] = None
         self.output_rank: Optional[int] = 0    # context-parallel runs: the rank that receives host arrays (None = all)
+        # passes per batched sampler run of generate_video_passes (None = all of them).  Batching pays when the per-GPU
+        # token count is small (4+ GPUs: full GEMM waves); with 1-2 GPUs one pass at a time is ~3 % faster under the power
+        # cap (alternating attention / GEMM phases), so `auto_pass_batch` picks by the size of the context-parallel group
+        self.pass_batch: Optional[int] = None
 
     def set_model_type(self, model_type: str):
         new = model_type.lower()
@@ -174,10 +178,16 @@ class CleanDiffusionRendererPipeline:
         B, _, T, H, W = video_tensor.shape
         state_shape = [self.config["latent_shape"][0], (T - 1) // 8 + 1, H // 8, W // 8]
         batch = self._move_to_device({k: v for k, v in data_batch.items() if k != "context_index"})
-        samples = model.generate_samples_multi(batch, context_indices, guidance=self.guidance, seed=effective_seed,
-                                               state_shape=state_shape, num_steps=self.num_steps)
         cp = getattr(model.net, "_cp", None)
         world, rank = (cp.world, cp.rank) if cp is not None and hasattr(cp, "group") else (1, 0)
+        per_run = self.pass_batch if self.pass_batch else (len(context_indices) if world >= 4 else 1)
+        samples, latent_condition = [], None
+        for i in range(0, len(context_indices), per_run):
+            samples.append(model.generate_samples_multi(batch, context_indices[i:i + per_run], guidance=self.guidance,
+                                                        seed=effective_seed, state_shape=state_shape, num_steps=self.num_steps,
+                                                        latent_condition=latent_condition))
+            latent_condition = batch["latent_condition"]          # the clip is tokenised once
+        samples = torch.cat(samples)
         frames = []
         for p, flag in enumerate(flags):
             if world == 1 or p % world == rank:

@@ -2,6 +2,7 @@
 stream out of torch, and call libdrb200.so.  PyTorch is used for memory and streams only — no math happens here."""
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
@@ -34,8 +35,9 @@ def _rows2d(t: torch.Tensor, name: str) -> int:
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_STORE,
-         resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, cta_group: int = 0) -> torch.Tensor:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T).  `a`, `w`, `out`, `resid` may be row-strided views."""
+         resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, cta_group: int = 0, sync=None) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T).  `a`, `w`, `out`, `resid` may be row-strided views.
+    `sync`: a drb_cp_sync descriptor (context_parallel.ContextParallel.sync) when `a` is filled by peer GPUs."""
     _req(a, "a"), _req(w, "w")
     M, K = a.shape
     N = w.shape[0]
@@ -50,8 +52,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, e
     if resid is not None:
         _req(resid, "resid"), _req(gate, "gate")
         ldr = _rows2d(resid, "resid")
-    _lib.call("drb_gemm_bf16", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), out.data_ptr(),
-              _rows2d(out, "out"), M, N, K, epilogue, _ptr(resid), ldr, _ptr(gate), cta_group, _stream())
+    if sync is None:
+        _lib.call("drb_gemm_bf16", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), out.data_ptr(),
+                  _rows2d(out, "out"), M, N, K, epilogue, _ptr(resid), ldr, _ptr(gate), cta_group, _stream())
+    else:
+        _lib.call("drb_gemm_bf16_sync", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), out.data_ptr(),
+                  _rows2d(out, "out"), M, N, K, epilogue, _ptr(resid), ldr, _ptr(gate), cta_group, ctypes.byref(sync), _stream())
     return out
 
 
@@ -351,7 +357,7 @@ def qk_norm_rope_scatter(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, 
 
 def attention_cp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, o_ptrs, ld_o: int, rows_per_rank: int,
                  col0: int, heads_per_batch: Optional[int] = None, batch_rows: int = 0,
-                 max_abs_logit: Optional[torch.Tensor] = None) -> None:
+                 max_abs_logit: Optional[torch.Tensor] = None, sync=None) -> None:
     """attention over the local heads and all tokens; output row r is stored to o_ptrs[r // rows_per_rank].  Batched
     sequences: `num_heads` = batch * heads_per_batch (b, h) pairs; sequence b lands at local row b * batch_rows + ..."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -361,7 +367,7 @@ def attention_cp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: i
         raise ValueError("q, k, v must share one row pitch")
     _lib.call("drb_attention_bf16_cp_batched", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _lib.ptr_array(o_ptrs), len(o_ptrs), ld_o,
               q.shape[0], k.shape[0], num_heads, rows_per_rank, col0, num_heads if heads_per_batch is None else heads_per_batch,
-              batch_rows, _bound_ptr(max_abs_logit), _stream())
+              batch_rows, _bound_ptr(max_abs_logit), None if sync is None else ctypes.byref(sync), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ environment maps (fp32)
@@ -400,7 +406,7 @@ def envmap_tonemap(img: torch.Tensor, H: int, W: int):
 
 def qkv_gemm_norm_rope(a: torch.Tensor, w: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos_tab: torch.Tensor,
                        sin_tab: torch.Tensor, out: Optional[torch.Tensor] = None, peer_ptrs=None, peer_ld: int = 0,
-                       row0: int = 0, batch: int = 1) -> Optional[torch.Tensor]:
+                       row0: int = 0, batch: int = 1, sync=None) -> Optional[torch.Tensor]:
     """[q | k | v] = a[M,K] @ w[3D,K]^T with per-head RMSNorm + RoPE of q, k in the GEMM epilogue.  Plain: rows go to
     out [M, 3D].  Context-parallel (`peer_ptrs`): head h's rows go to peer_ptrs[h // (H/P)] at row row0 + s (no `out`).
     `batch` sequences of M / batch rows each are stacked along M (cos/sin tables repeated per sequence)."""
@@ -424,7 +430,7 @@ def qkv_gemm_norm_rope(a: torch.Tensor, w: torch.Tensor, wq: torch.Tensor, wk: t
         raise ValueError("the rows do not split into `batch` equal sequences")
     _lib.call("drb_gemm_qkv_norm_rope_batched", a.data_ptr(), _rows2d(a, "a"), w.data_ptr(), _rows2d(w, "w"), None, 0, M, D, K,
               wq.data_ptr(), wk.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), _lib.ptr_array(peer_ptrs), len(peer_ptrs),
-              peer_ld, row0, batch, M // batch, _stream())
+              peer_ld, row0, batch, M // batch, None if sync is None else ctypes.byref(sync), _stream())
     return None
 
 

@@ -34,6 +34,24 @@ extern "C" {
 #define DRB_EPI_QKV_NORM_ROPE 3  /* internal to drb_gemm_qkv_norm_rope                                                      */
 
 #define DRB_CP_MAX_RANKS 8 /* GPUs of one context-parallel group */
+#define DRB_CP_FLAG_SLOTS 4   /* flag array of a rank: uint32 [DRB_CP_FLAG_SLOTS][DRB_CP_MAX_RANKS] + status, 256 bytes */
+#define DRB_CP_STATUS_WORD 63 /* local flag word set to 1 when an in-kernel wait timed out                          */
+
+/* Cross-GPU ordering folded into a kernel (context parallelism, csrc/cp_sync.cuh).  flag_ptrs[j] = rank j's peer-mapped,
+ * zeroed flag array.  wait_epoch != 0: the kernel's operand-loading thread first waits until word [wait_slot][r] of the
+ * LOCAL array is >= wait_epoch for every rank r — the peers' P2P stores into this GPU's input buffer have landed.
+ * signal_epoch != 0: once every CTA of the kernel has fenced its stores, the last one writes word [signal_slot][rank] =
+ * signal_epoch into every rank's array; `counter` is a local, zero-initialised uint32 (reset by the kernel).  Epochs
+ * increase per slot and are identical on all ranks.  timeout_ms = 0 means 60 s; on a timeout the kernel sets the local
+ * status word and carries on (the host checks it) instead of trapping. */
+typedef struct drb_cp_sync {
+  void* const* flag_ptrs;
+  uint32_t* counter;
+  int world, rank;
+  int signal_slot, wait_slot;
+  uint32_t signal_epoch, wait_epoch;
+  uint32_t timeout_ms;
+} drb_cp_sync;
 
 const char* drb_last_error(void);
 int drb_version(void);
@@ -49,6 +67,11 @@ int drb_device_supported(void);
 int drb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                   int M, int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
                   int cta_group, void* stream);
+/* The same, with cross-GPU ordering folded in: under context parallelism the out-projection's A operand is the buffer the
+ * peers' attention epilogues store into, so its TMA producer waits for their flags (sync->wait_*) before the first load. */
+int drb_gemm_bf16_sync(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                       int M, int N, int K, int epilogue, const void* resid, int64_t ldr, const void* gate,
+                       int cta_group, const drb_cp_sync* sync, void* stream);
 
 /* Ring form (context parallelism when heads are not split: every GPU keeps its query rows and visits the K/V blocks of
  * all GPUs in ring order): one launch = one K/V block.  Running state per (row, head): state_ml [q_len, H, 2] fp32 =
@@ -72,11 +95,12 @@ int drb_gemm_qkv_norm_rope(const void* A, int64_t lda, const void* W, int64_t ld
  * as ONE GEMM, so the weights stream once per batch and the tile grid has no short last wave at M = S/P.  cos_tab /
  * sin_tab are [M,128] (the per-sequence table repeated).  world > 0: sequence b, head h, token s goes to row row0 + s of
  * the owner's [S, peer_ld] buffer at column (sect*batch + b)*(H/world)*128 + (h mod H/world)*128, sect = 0 q, 1 k, 2 v —
- * i.e. (b, h) pairs look like batch*(H/world) heads to drb_attention_bf16_cp_batched.  rows_per_batch >= 32. */
+ * i.e. (b, h) pairs look like batch*(H/world) heads to drb_attention_bf16_cp_batched.  rows_per_batch >= 32.
+ * `sync` (nullable): the last CTA signals "all q / k / v rows of this rank are stored" (sync->signal_*). */
 int drb_gemm_qkv_norm_rope_batched(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int D,
                                    int K, const void* wq, const void* wk, const void* cos_tab, const void* sin_tab,
                                    void* const* peer_ptrs, int world, int64_t peer_ld, int row0, int batch, int rows_per_batch,
-                                   void* stream);
+                                   const drb_cp_sync* sync, void* stream);
 
 /* ---- self-attention ------------------------------------------------------------------------------------------
  * o[s, h*128 + d] = softmax_j(q[s,h,:]·k[j,h,:] / sqrt(128)) v[j,h,d]; no mask, no dropout, head_dim 128.
@@ -106,10 +130,12 @@ int drb_attention_bf16_cp(const void* q, const void* k, const void* v, int64_t l
 /* Batched sequences (see drb_gemm_qkv_norm_rope_batched): num_heads = batch * heads_per_batch attention problems over the
  * same token range; "head" g = b*heads_per_batch + h reads column g*128 of q / k / v and its output row r is stored at
  * local row b*batch_rows + (r mod rows_per_rank), column col0 + h*128, of the owner's [batch*batch_rows, ld_o] buffer.
- * max_abs_logit: as drb_attention_bf16_bounded. */
+ * max_abs_logit: as drb_attention_bf16_bounded.  `sync` (nullable): wait for the peers' q / k / v stores before the first
+ * load (sync->wait_*) and signal "all output rows of this rank are stored" from the last CTA (sync->signal_*). */
 int drb_attention_bf16_cp_batched(const void* q, const void* k, const void* v, int64_t ld_qkv, void* const* o_peers, int world,
                                   int64_t ld_o, int q_len, int kv_len, int num_heads, int rows_per_rank, int col0,
-                                  int heads_per_batch, int batch_rows, const float* max_abs_logit, void* stream);
+                                  int heads_per_batch, int batch_rows, const float* max_abs_logit, const drb_cp_sync* sync,
+                                  void* stream);
 
 /* ---- fused elementwise family ----------------------------------------------------------------------------------
  * AdaLN: out = bf16(bf16(bf16(LN(x)) * bf16(1+scale)) + shift), LN over `D` without affine, eps 1e-6, fp32 stats

@@ -16,6 +16,8 @@ def main():
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--ring", action="store_true", help="ring K/V schedule instead of the Ulysses head exchange")
+    ap.add_argument("--batch", default="1", help="--full: G-buffer passes batched along the token rows (comma-separated list)")
+    ap.add_argument("--steps", type=int, default=6)
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -49,6 +51,11 @@ def main():
             xt = x * model.scheduler.sigmas[0]
             ref_z = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci}, None)
             model.net.enable_context_parallel(cp)
+            if not args.ring:          # the A/B flavour first: stand-alone barrier kernels instead of in-kernel flag waits
+                cp.fused_sync = False
+                got_b = model.net(x=x, timesteps=sigma, latent_condition=cond, context_index=ci)
+                cp.fused_sync = True
+                ok = ok and bool(torch.equal(got_b, ref))
             got = model.net(x=x, timesteps=sigma, latent_condition=cond, context_index=ci)
             got_z = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci}, None)
             got_g = model.sample_latent(xt, {"latent_condition": cond, "context_index": ci},
@@ -64,7 +71,8 @@ def main():
         else:
             e = [bool(torch.equal(got, ref)), bool(torch.equal(got_z, ref_z)), bool(torch.equal(got_g, ref_g))]
             print(f"rank {rank}/{world}: forward identical={e[0]} sampler identical={e[1]} cfg sampler identical={e[2]}", flush=True)
-            ok = all(e)
+            ok = ok and all(e)
+        cp.check()
     if args.full:
         cfg = cfgm.get_inverse_renderer_config(704, 1280, 57)
         cfg["model_type"] = "inverse"
@@ -76,34 +84,45 @@ def main():
         net._ensure_packed()
         T, H, W = 8, 88, 160
         Tl = T // world
-        ws = net._workspace(Tl, H, W, dev, cp)
         g = torch.Generator(device=dev).manual_seed(1234)
         cond = (torch.randn(1, 16, T, H, W, device=dev, generator=g) * 0.5).bfloat16()
         model.scheduler.set_timesteps(15, device=dev)
         sig = model.scheduler.sigmas.contiguous()
-        x = (torch.randn(16, T, H, W, device=dev, generator=g).bfloat16() * sig[0]).bfloat16()[:, rank * Tl:(rank + 1) * Tl].contiguous()
-        net.prepare_condition(ws, cond[:, :, rank * Tl:(rank + 1) * Tl], Tl, H, W)
-        use_ca = net.prepare_context(ws, net.context_token(torch.zeros(1, 1, dtype=torch.long, device=dev)))
-        for fused in ((True,) if args.ring else (True, False, True, False)):
-            net.fuse_qkv_epilogue = fused
-            for i in range(3):
-                net.denoise_step(ws, x, sig[i:i + 1], sig[i + 1:i + 2], use_ca)
-            dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n = 6
-            e0.record()
-            for i in range(n):
-                net.denoise_step(ws, x, sig[3 + i:4 + i], sig[4 + i:5 + i], use_ca)
-            e1.record()
-            dist.barrier()
-            torch.cuda.synchronize()
-            ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            if rank == 0:
-                what = "ring K/V schedule over peer memory" if args.ring else f"QKV all-to-all {'in the GEMM epilogue' if fused else 'as a scatter kernel'}"
-                print(f"CP{world} 7B denoise step 57x704x1280, {what}: "
-                      f"{ms.item():.1f} ms/step (max over ranks), finite={bool(torch.isfinite(x.float()).all())}", flush=True)
+        x1 = (torch.randn(16, T, H, W, device=dev, generator=g).bfloat16() * sig[0]).bfloat16()[:, rank * Tl:(rank + 1) * Tl]
+        for B in [int(v) for v in args.batch.split(",")]:
+            ws = net._workspace(Tl, H, W, dev, cp, batch=B)
+            x = x1.unsqueeze(0).expand(B, -1, -1, -1, -1).contiguous()
+            for b in range(B):
+                net.prepare_condition(ws, cond[:, :, rank * Tl:(rank + 1) * Tl], Tl, H, W, b)
+                use_ca = net.prepare_context(ws, net.context_token(torch.full((1, 1), b % 5, dtype=torch.long, device=dev)), b)
+            # (QKV exchange fused in the GEMM epilogue?, ordering by in-kernel flags?)
+            variants = [(True, False)] if args.ring else [(True, True), (True, False), (True, True), (True, False)]
+            if B == 1 and not args.ring:
+                variants.append((False, False))
+            for fused, flags in variants:
+                net.fuse_qkv_epilogue, cp.fused_sync = fused, flags
+                for i in range(3):
+                    net.denoise_step(ws, x, sig[i:i + 1], sig[i + 1:i + 2], use_ca)
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = args.steps
+                e0.record()
+                for i in range(n):
+                    net.denoise_step(ws, x, sig[3 + i:4 + i], sig[4 + i:5 + i], use_ca)
+                e1.record()
+                dist.barrier()
+                torch.cuda.synchronize()
+                ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    what = ("ring K/V schedule over peer memory" if args.ring else
+                            f"QKV all-to-all {'in the GEMM epilogue' if fused else 'as a scatter kernel'}, "
+                            f"{'flag waits inside the kernels' if flags else 'stand-alone barrier kernels'}")
+                    print(f"CP{world} 7B denoise step 57x704x1280, {B} batched pass(es), {what}: {ms.item():.1f} ms/iteration = "
+                          f"{ms.item() / B:.2f} ms/step (max over ranks), finite={bool(torch.isfinite(x.float()).all())}", flush=True)
+            cp.check()
+        cp.fused_sync = not args.ring
         net.fuse_qkv_epilogue = True
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
