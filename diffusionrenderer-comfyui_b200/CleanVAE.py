@@ -113,6 +113,10 @@ class AutoencoderKLCosmos(nn.Module):
         super().__init__()
         cfg = dict(DEFAULT_CONFIG)
         cfg.update({k: v for k, v in config.items() if k in DEFAULT_CONFIG})
+        # per-(channel, latent frame) statistics of a 16-latent-frame chunk (VAE_config.json:21-536): not part of the network,
+        # used only by the opt-in per-chunk normalisation of CleanVAE.encode_chunked / decode_chunked
+        cfg["latents_mean"] = list(config["latents_mean"]) if config.get("latents_mean") is not None else None
+        cfg["latents_std"] = list(config["latents_std"]) if config.get("latents_std") is not None else None
         if cfg["patch_type"] != "haar" or cfg["patch_size"] != 4:
             raise ValueError("only the Haar patcher with patch_size 4 is implemented (CV8x8x8)")
         self.config = SimpleNamespace(**cfg)
@@ -476,8 +480,25 @@ class CleanVAE:
             raise ValueError(f"pixel_chunk_duration {pixel_chunk_duration} must be 1 + a multiple of {factor}")
         return (pixel_chunk_duration - 1) // factor + 1
 
+    def _chunk_stats(self, frames: int, repeat: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """bf16 (mean, std), one per (chunk, channel, latent frame) row: the config's latents_mean / latents_std viewed as
+        (C, -1) and cut to the chunk's frame count (the layout diffusers' Cosmos pipelines use), repeated per chunk"""
+        mean, std = getattr(self.config, "latents_mean", None), getattr(self.config, "latents_std", None)
+        if mean is None or std is None:
+            raise ValueError("the tokenizer config carries no latents_mean / latents_std (VAE_config.json:21-536)")
+        C = self.latent_ch
+        m = torch.tensor(mean, dtype=torch.float32).reshape(C, -1)
+        sd = torch.tensor(std, dtype=torch.float32).reshape(C, -1)
+        if m.shape[1] < frames:
+            raise ValueError(f"the config holds statistics for {m.shape[1]} latent frames per chunk, the chunk has {frames}")
+        to = lambda t: t[:, :frames].reshape(1, -1).repeat(repeat, 1).reshape(-1).to(device=device, dtype=torch.bfloat16).contiguous()
+        return to(m), to(sd)
+
     @torch.no_grad()
-    def encode_chunked(self, state_5d: torch.Tensor, pixel_chunk_duration: int = 121) -> torch.Tensor:
+    def encode_chunked(self, state_5d: torch.Tensor, pixel_chunk_duration: int = 121, normalize: bool = False,
+                       max_enc_batch_size: int = 8) -> torch.Tensor:
+        """`normalize`: apply the per-chunk latent statistics, (z - mean) / std per (channel, latent frame)
+        (pretrained_vae.py:142); at most `max_enc_batch_size` chunks go through the tokenizer per call (:389-405)."""
         if state_5d.ndim != 5:
             raise ValueError(f"CleanVAE expects a 5D input (B, C, T, H, W), but got {state_5d.shape}")
         B, C, T, H, W = state_5d.shape
@@ -486,12 +507,19 @@ class CleanVAE:
             raise ValueError(f"Temporal dimension {T} is not divisible by chunk_length {pixel_chunk_duration}")
         n = T // pixel_chunk_duration
         chunks = state_5d.reshape(B, C, n, pixel_chunk_duration, H, W).permute(0, 2, 1, 3, 4, 5).reshape(B * n, C, pixel_chunk_duration, H, W)
-        z = self.encode(chunks)                                                   # (B*n, 16, t, h, w)
+        step = max(1, int(max_enc_batch_size))
+        z = torch.cat([self.encode(chunks[i:i + step]) for i in range(0, B * n, step)], dim=0)      # (B*n, 16, t, h, w)
         _, c, t, h, w = z.shape
+        if normalize:
+            mean, std = self._chunk_stats(t, B * n, z.device)
+            z = ops.latent_normalize(z.contiguous(), mean, std, decode=False)
         return z.reshape(B, n, c, t, h, w).permute(0, 2, 1, 3, 4, 5).reshape(B, c, n * t, h, w)
 
     @torch.no_grad()
-    def decode_chunked(self, latent_5d: torch.Tensor, pixel_chunk_duration: int = 121) -> torch.Tensor:
+    def decode_chunked(self, latent_5d: torch.Tensor, pixel_chunk_duration: int = 121, normalize: bool = False,
+                       max_dec_batch_size: int = 4) -> torch.Tensor:
+        """`normalize`: undo the per-chunk latent statistics first, z * std + mean (pretrained_vae.py:150); at most
+        `max_dec_batch_size` chunks go through the tokenizer per call (:424-433)."""
         if latent_5d.ndim != 5:
             raise ValueError(f"CleanVAE expects a 5D latent (B, C, T, H, W), but got {latent_5d.shape}")
         B, c, T, h, w = latent_5d.shape
@@ -500,7 +528,11 @@ class CleanVAE:
             raise ValueError(f"Temporal dimension {T} is not divisible by chunk_length {lc}")
         n = T // lc
         chunks = latent_5d.reshape(B, c, n, lc, h, w).permute(0, 2, 1, 3, 4, 5).reshape(B * n, c, lc, h, w)
-        y = self.decode(chunks)                                                   # (B*n, 3, pixel_chunk_duration, H, W)
+        if normalize:
+            mean, std = self._chunk_stats(lc, B * n, chunks.device)
+            chunks = ops.latent_normalize(chunks.to(torch.bfloat16).contiguous(), mean, std, decode=True)
+        step = max(1, int(max_dec_batch_size))
+        y = torch.cat([self.decode(chunks[i:i + step]) for i in range(0, B * n, step)], dim=0)      # (B*n, 3, pixel_chunk_duration, H, W)
         _, C, t, H, W = y.shape
         return y.reshape(B, n, C, t, H, W).permute(0, 2, 1, 3, 4, 5).reshape(B, C, n * t, H, W)
 

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "drb_temporal_attention_cl": [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p],
     "drb_planar_to_cl": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],
     "drb_cl_to_planar": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],
+    "drb_latent_normalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p],
     "drb_envmap_latlong_to_cubemap": [c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_int, c_void_p],
     "drb_envmap_project": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "drb_envmap_tonemap": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],

@@ -32,10 +32,13 @@ def sources():
 
 
 def _digest(paths) -> str:
+    """content hash of the sources, keyed by their path RELATIVE to the repository (the stamp must survive the tree being
+    copied to another directory — the GPU box receives a snapshot under a scratch path)"""
     h = hashlib.sha256()
-    for p in sorted(paths):
+    root = os.path.dirname(HERE)
+    for p in sorted(paths, key=lambda q: os.path.relpath(q, root)):
         with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
+            h.update(os.path.relpath(p, root).encode() + b"\0" + f.read())
     h.update(" ".join(ARCH_FLAGS + NVCC_FLAGS).encode())
     return h.hexdigest()
 
@@ -49,7 +52,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     digest = _digest(deps)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
-    nvcc = _nvcc()
+    try:
+        nvcc = _nvcc()
+    except RuntimeError:
+        if os.path.exists(LIB) and not force:   # a box without the toolkit: use the library that travelled with the tree
+            sys.stderr.write(f"build.py: nvcc not found and the source stamp does not match; reusing the existing {LIB}\n")
+            return LIB
+        raise
     os.makedirs(OBJ_DIR, exist_ok=True)
 
     def compile_one(src):

@@ -559,6 +559,38 @@ extern "C" int drb_planar_to_cl(const void* x, void* out, int C, int Cpad, int64
   return 0;
 }
 
+// Per-chunk latent statistics of the chunking tokenizer (pretrained_vae.py:131-152): one (mean, std) per row of `hw` values.
+//   mode 0 (after encode):  out = bf16(bf16(x - mean) / std)        (:142)
+//   mode 1 (before decode): out = bf16(bf16(x * std) + mean)        (:150)   — both in the bf16 arithmetic of the reference
+namespace drb {
+namespace {
+__global__ void __launch_bounds__(256)
+latent_normalize_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ mean,
+                        const __nv_bfloat16* __restrict__ stdv, __nv_bfloat16* __restrict__ out, int64_t hw, int mode) {
+  const int row = blockIdx.y;
+  const float m = __bfloat162float(mean[row]), s = __bfloat162float(stdv[row]);
+  const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * hw;
+  __nv_bfloat16* orow = out + static_cast<int64_t>(row) * hw;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < hw; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = __bfloat162float(xr[i]);
+    const float o = mode == 0 ? __bfloat162float(__float2bfloat16_rn(v - m)) / s : __bfloat162float(__float2bfloat16_rn(v * s)) + m;
+    orow[i] = __float2bfloat16_rn(o);
+  }
+}
+}  // namespace
+}  // namespace drb
+
+extern "C" int drb_latent_normalize(const void* x, const void* mean, const void* stdv, void* out, int rows, int64_t hw, int mode,
+                                    void* stream) {
+  DRB_REQUIRE(x && mean && stdv && out, "null pointer");
+  DRB_REQUIRE(rows > 0 && rows <= 65535 && hw > 0 && (mode == 0 || mode == 1), "bad sizes or mode");
+  int gx = static_cast<int>((hw + 255) / 256);
+  if (gx > 64) gx = 64;
+  latent_normalize_kernel<<<dim3(gx, rows), 256, 0, STREAM>>>(CBF(x), CBF(mean), CBF(stdv), BF(out), hw, mode);
+  DRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int drb_cl_to_planar(const void* in, void* out, int C, int Cpad, int64_t thw, float scale, void* stream) {
   DRB_REQUIRE(in && out, "null pointer");
   DRB_REQUIRE(C > 0 && Cpad >= C && thw > 0, "Cpad must be >= C");

@@ -50,6 +50,16 @@ def latlong_vec(res, device=None):
     return torch.stack((sintheta * sinphi, costheta, -sintheta * cosphi), dim=-1)
 
 
+def _net_dims_from_state_dict(sd, defaults) -> dict:
+    """model_channels / num_blocks / num_heads of the GeneralDIT a checkpoint holds (head_dim is 128)"""
+    w = sd.get("net.affline_norm.weight")
+    if w is None:
+        return {}
+    D = int(w.shape[0])
+    blocks = {k.split(".")[2] for k in sd if k.startswith("net.blocks.block")}
+    return {"model_channels": D, "num_blocks": len(blocks) or defaults["num_blocks"], "num_heads": D // 128}
+
+
 class LoadDiffusionRendererModel:
     @classmethod
     def INPUT_TYPES(s):
@@ -77,9 +87,11 @@ class LoadDiffusionRendererModel:
         sd = comfy.utils.load_torch_file(ckpt, safe_load=True)
         if "model" in sd:
             sd = sd["model"]
-        # the checkpoint tells which renderer it is: only the inverse net has a context embedding
+        # the checkpoint tells which renderer it is: only the inverse net has a context embedding — and how
+        # large the net is (the released checkpoints are the 7B FADITV2 net of the reference config, nodes.py:94-96)
         from .diffusion_renderer_config import get_forward_renderer_config
         cfg = get_inverse_renderer_config() if "net.context_embedding.weight" in sd else get_forward_renderer_config()
+        cfg["net"].update(_net_dims_from_state_dict(sd, cfg["net"]))
         with torch.device("meta"):
             m = CleanDiffusionRendererModel(cfg)
         m.to_empty(device=device)

@@ -344,6 +344,20 @@ def cl_to_planar(x: torch.Tensor, C: int, scale: float = 1.0) -> torch.Tensor:
     return out
 
 
+def latent_normalize(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, decode: bool) -> torch.Tensor:
+    """x (..., H, W) bf16 contiguous with one (mean, std) per leading index; encode: (x - mean) / std, decode: x * std + mean"""
+    _req(x, "x"), _req(mean, "mean"), _req(std, "std")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    rows = mean.numel()
+    hw = x.shape[-1] * x.shape[-2]
+    if std.numel() != rows or x.numel() != rows * hw or not mean.is_contiguous() or not std.is_contiguous():
+        raise ValueError("one (mean, std) pair per (batch, channel, frame) row of x")
+    out = torch.empty_like(x)
+    _lib.call("drb_latent_normalize", x.data_ptr(), mean.data_ptr(), std.data_ptr(), out.data_ptr(), rows, hw, int(bool(decode)), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ context parallelism
 def qk_norm_rope_scatter(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor,
                          num_heads: int, dst_ptrs, dst_ld: int, row0: int) -> None:

@@ -17,17 +17,24 @@ CUBEMAP_RES = 512      # "official 512x512 cubemap" (reference :316)
 
 
 class EnvironmentMapCache:
-    """result cache keyed by (content hash, resolution, format, brightness, flip, rotation) (reference :23-66)"""
+    """LRU cache keyed by (content hash, resolution, format, brightness, flip, rotation, device) (reference :23-66).  It
+    holds the un-expanded (H,W,3) tone-mapped pair; the frame axis is added after the lookup, so the same environment map
+    can serve clips of different length (the reference caches the expanded result and returns a stale frame count)."""
 
     def __init__(self, max_size: int = 10):
-        self.cache: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self.cache: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.max_size = max_size
 
     def get(self, key):
-        return self.cache.get(key)
+        value = self.cache.get(key)
+        if value is not None:                       # most recently used goes last
+            self.cache[key] = self.cache.pop(key)
+        return value
 
     def put(self, key, value) -> None:
-        if len(self.cache) >= self.max_size:
+        if key in self.cache:
+            self.cache.pop(key)
+        elif len(self.cache) >= self.max_size:      # evict the least recently used entry, only for a NEW key
             self.cache.pop(next(iter(self.cache)))
         self.cache[key] = value
 
@@ -104,41 +111,41 @@ def _frames(ldr: torch.Tensor, lg: torch.Tensor, num_frames: int) -> Dict[str, t
     return {"env_ldr": ldr.unsqueeze(0), "env_log": lg.unsqueeze(0)}
 
 
-def _key(env_input, resolution, fmt, brightness, flip, rot):
+def _key(env_input, resolution, fmt, brightness, flip, rot, device):
     h = compute_tensor_hash(env_input) if isinstance(env_input, torch.Tensor) else hashlib.md5(str(env_input).encode()).hexdigest()
-    return (h, tuple(resolution), fmt, float(brightness), bool(flip), float(rot))
+    return (h, tuple(resolution), fmt, float(brightness), bool(flip), float(rot), str(torch.device(device)))
 
 
 def render_projection_from_panorama(env_input: Union[str, torch.Tensor], resolution: Tuple[int, int], env_brightness: float = 1.0,
                                     env_flip: bool = True, env_rot: float = 180.0, device="cuda", num_frames: int = 1,
                                     use_cache: bool = True, **kwargs) -> Dict[str, torch.Tensor]:
     """panorama -> cube map -> projected view -> {'env_ldr', 'env_log'}: (T,H,W,3) in [0,1] (reference :408-467)"""
-    key = _key(env_input, resolution, "proj", env_brightness, env_flip, env_rot) if use_cache else None
-    if key is not None and _env_cache.get(key) is not None:
-        return _env_cache.get(key)
+    key = _key(env_input, resolution, "proj", env_brightness, env_flip, env_rot, device) if use_cache else None
+    hit = _env_cache.get(key) if key is not None else None
+    if hit is not None:
+        return _frames(hit[0], hit[1], num_frames)
     H, W = resolution
     pano = _source(env_input, device)
     roll = int(pano.shape[1] * env_rot / 360) if env_rot != 0 else 0          # reference :282-284
     cube = ops.envmap_latlong_to_cubemap(pano, env_brightness, env_flip, roll, CUBEMAP_RES)
     ldr, lg = ops.envmap_project(cube, H, W)
-    result = _frames(ldr, lg, num_frames)
     if key is not None:
-        _env_cache.put(key, result)
-    return result
+        _env_cache.put(key, (ldr, lg))
+    return _frames(ldr, lg, num_frames)
 
 
 def tonemap_image_direct(env_input: Union[str, torch.Tensor], resolution: Tuple[int, int], device="cuda", num_frames: int = 1,
                          use_cache: bool = True, **kwargs) -> Dict[str, torch.Tensor]:
     """pre-rendered HDR probe image -> resize + tone mapping (reference :469-526)"""
-    key = _key(env_input, resolution, "ball", 1.0, False, 0.0) if use_cache else None
-    if key is not None and _env_cache.get(key) is not None:
-        return _env_cache.get(key)
+    key = _key(env_input, resolution, "ball", 1.0, False, 0.0, device) if use_cache else None
+    hit = _env_cache.get(key) if key is not None else None
+    if hit is not None:
+        return _frames(hit[0], hit[1], num_frames)
     H, W = resolution
     ldr, lg = ops.envmap_tonemap(_source(env_input, device), H, W)
-    result = _frames(ldr, lg, num_frames)
     if key is not None:
-        _env_cache.put(key, result)
-    return result
+        _env_cache.put(key, (ldr, lg))
+    return _frames(ldr, lg, num_frames)
 
 
 def clear_environment_cache() -> None:

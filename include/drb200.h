@@ -262,6 +262,11 @@ int drb_temporal_attention_cl(const void* qkv, void* out, int T, int64_t hw, int
 int drb_planar_to_cl(const void* x, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
 int drb_cl_to_planar(const void* in, void* out, int C, int Cpad, int64_t thw, float scale, void* stream);
 
+/* Per-chunk latent statistics of the upstream chunking tokenizer (pretrained_vae.py:131-152, unused by the reference's
+ * live path): x, out bf16 [rows][hw]; mean, std bf16 [rows] (one pair per (batch, channel, latent frame) row).
+ * mode 0 (after encode): out = bf16(bf16(x - mean) / std) (:142); mode 1 (before decode): out = bf16(bf16(x * std) + mean) (:150). */
+int drb_latent_normalize(const void* x, const void* mean, const void* std, void* out, int rows, int64_t hw, int mode, void* stream);
+
 /* ==== environment-map conditioning of the forward renderer ===================================
  * The reference projects the panorama with nvdiffrast (preprocess_envmap.py); these entry points do it on the device
  * without it.  fp32, channels-last RGB.

@@ -51,9 +51,13 @@ def test_module_entry_points_match_oracle_and_cache():
     assert out["env_ldr"].shape == out["env_log"].shape == (5, 64, 96, 3)
     close(out["env_ldr"][0], ref["env_ldr"])
     close(out["env_log"][3], ref["env_log"])
-    assert pe.render_projection_from_panorama(image, (64, 96), env_brightness=1.2, env_flip=True, env_rot=180.0, device=DEV,
-                                              num_frames=5) is out          # cache hit
+    hit = pe.render_projection_from_panorama(image, (64, 96), env_brightness=1.2, env_flip=True, env_rot=180.0, device=DEV, num_frames=5)
+    assert hit["env_ldr"].data_ptr() == out["env_ldr"].data_ptr()            # cache hit: the same device tensor, re-expanded
     assert pe.get_cache_stats()["cache_size"] == 1
+    # the same environment map for a clip of another length: the cached pair is expanded to the new frame count (the
+    # reference caches the expanded result and would hand back 5 frames here)
+    other = pe.render_projection_from_panorama(image, (64, 96), env_brightness=1.2, env_flip=True, env_rot=180.0, device=DEV, num_frames=3)
+    assert other["env_ldr"].shape == (3, 64, 96, 3) and pe.get_cache_stats()["cache_size"] == 1
     # the direct path has no NaN / Inf clean-up in the reference (:469-526): use a clean probe image
     src = torch.nan_to_num(src, nan=0.5, posinf=100.0)
     image = src.unsqueeze(0).cpu()

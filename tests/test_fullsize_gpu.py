@@ -1,4 +1,5 @@
-"""Full-size parity (BASELINE.json configs[1]: 7B GeneralDIT, 57x704x1280 clip, S = 28 160 tokens) against the oracle run
+"""Full-size parity (BASELINE.json configs[1] and [2]: the 7B inverse renderer and the 7B forward renderer — 136 condition
+channels, K = 612 -> 616 patch GEMM, no context embedding — on a 57x704x1280 clip, S = 28 160 tokens) against the oracle run
 in bf16 on the same GPU with the very same weight tensors: teacher-forced latent after one Euler step, relative L2
 <= 1e-2 (north_star), at the first, a middle and the last sigma of the 15-step schedule.  The raw network output F is
 printed but not gated: at 28 blocks the reference's own bf16-vs-fp32 noise on F is 1.2e-2..1.7e-2.
@@ -9,26 +10,27 @@ import torch
 
 from oracle import sampler_oracle as so
 from oracle.dit_oracle import dit_forward
-from oracle.weights import FULL_INVERSE
+from oracle.weights import FULL_FORWARD, FULL_INVERSE
 from tests.util import rel_l2
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.fixture(scope="module")
-def full_model():
+@pytest.fixture(scope="module", params=["inverse", "forward"])
+def full_model(request):
     if torch.cuda.get_device_properties(0).total_memory < 60 * 2 ** 30:
         pytest.skip("needs ~40 GiB of device memory")
     from drb200 import diffusion_renderer_config as cfgm
     from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
-    cfg = cfgm.get_inverse_renderer_config(704, 1280, 57)
-    cfg["model_type"] = "inverse"
+    cfg = cfgm.get_config_by_model_type(request.param, 704, 1280, 57)   # diffusion_renderer_config.py:131-170 / :191-233
+    cfg["model_type"] = request.param
     with torch.device("meta"):
         model = CleanDiffusionRendererModel(cfg)
     model = model.to_empty(device=DEV).to(torch.bfloat16)
     model.net.init_weights_(seed=0)
     model.net._ensure_packed()                     # parameters now view the packed buffers: the oracle reads the same bytes
+    model.kind = request.param
     yield model
     del model
     torch.cuda.empty_cache()
@@ -36,27 +38,30 @@ def full_model():
 
 def test_full_size_euler_step_matches_oracle(full_model):
     model = full_model
+    dims = FULL_INVERSE if model.kind == "inverse" else FULL_FORWARD
     sdn = {k: v for k, v in model.net.state_dict().items()}
     T, H, W = 8, 88, 160
     g = torch.Generator(device=DEV).manual_seed(1234)
-    cond = (torch.randn(1, 16, T, H, W, device=DEV, generator=g) * 0.5).bfloat16()
+    cond = (torch.randn(1, dims.additional_concat_ch, T, H, W, device=DEV, generator=g) * 0.5).bfloat16()
+    if model.kind == "forward":                  # every 17th channel is a condition mask of ones (model:191-196)
+        cond[:, 16::17] = 1.0
     ci = torch.full((1, 1), 3, dtype=torch.long, device=DEV)
     sig = so.sigma_schedule(15, device=DEV)
     model.scheduler.set_timesteps(15, device=DEV)
     noise = torch.randn(1, 16, T, H, W, device=DEV, generator=g).bfloat16()
     for i in (0, 7, 14):
         # a plausible x_t for this sigma: clean-latent-like signal (std 0.5) plus noise at sigma
-        x_t = (cond.float() + noise.float() * sig[i]).bfloat16()
+        x_t = (cond[:, :16].float() + noise.float() * sig[i]).bfloat16()
         with torch.no_grad():
             x_in = so.scale_model_input(x_t, sig[i])
-            f_ref = dit_forward(sdn, FULL_INVERSE, x_in, sig[i], cond, ci)
+            f_ref = dit_forward(sdn, dims, x_in, sig[i], cond, ci)
             x_ref = so.euler_step(f_ref, sig[i], sig[i + 1], x_t)
             f_got = model.net(x=x_in, timesteps=sig[i], latent_condition=cond, context_index=ci)
             steps = []
             model.sample_latent(x_t, {"latent_condition": cond, "context_index": ci}, None, per_step=steps,
                                 teacher=[x_t] * 15)     # teacher-forced: every step restarts from x_t; take step i
         e_x, e_f = rel_l2(steps[i], x_ref), rel_l2(f_got, f_ref)
-        print(f"\nsigma[{i}] = {float(sig[i]):.3f}: latent after the Euler step rel-L2 {e_x:.3e}; network output F rel-L2 {e_f:.3e}")
+        print(f"\n{model.kind} renderer, sigma[{i}] = {float(sig[i]):.3f}: latent after the Euler step rel-L2 {e_x:.3e}; network output F rel-L2 {e_f:.3e}")
         assert torch.isfinite(f_got.float()).all()
         assert e_x <= 1e-2
 
@@ -67,7 +72,7 @@ def test_full_size_forward_is_deterministic_and_euler_is_linear_in_f(full_model)
     T, H, W = 8, 88, 160
     g = torch.Generator(device=DEV).manual_seed(7)
     x = torch.randn(1, 16, T, H, W, device=DEV, generator=g).bfloat16()
-    cond = (torch.randn(1, 16, T, H, W, device=DEV, generator=g) * 0.5).bfloat16()
+    cond = (torch.randn(1, model.net.additional_concat_ch, T, H, W, device=DEV, generator=g) * 0.5).bfloat16()
     ci = torch.full((1, 1), 1, dtype=torch.long, device=DEV)
     s = torch.tensor(1.26, device=DEV)
     with torch.no_grad():

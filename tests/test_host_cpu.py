@@ -207,11 +207,19 @@ def test_envmap_module_host_logic():
     assert pe.process_comfyui_tensor(torch.zeros(16, 32, 1)).shape == (16, 32, 3)
     a, b = torch.rand(1, 8, 16, 3), torch.rand(1, 8, 16, 3)
     assert pe.compute_tensor_hash(a) == pe.compute_tensor_hash(a.clone()) != pe.compute_tensor_hash(b)
-    assert pe._key(a, (4, 8), "proj", 1.0, True, 180.0) != pe._key(a, (4, 8), "proj", 1.5, True, 180.0)
+    assert pe._key(a, (4, 8), "proj", 1.0, True, 180.0, "cuda") != pe._key(a, (4, 8), "proj", 1.5, True, 180.0, "cuda")
+    assert pe._key(a, (4, 8), "proj", 1.0, True, 180.0, "cuda:0") != pe._key(a, (4, 8), "proj", 1.0, True, 180.0, "cuda:1")
     cache = pe.EnvironmentMapCache(max_size=2)
     for i in range(3):
         cache.put(("k", i), {"env_ldr": i})
     assert cache.get(("k", 0)) is None and cache.get(("k", 2)) == {"env_ldr": 2}
+    # LRU, and overwriting an existing key evicts nothing
+    assert cache.get(("k", 1)) == {"env_ldr": 1}          # 1 is now the most recently used
+    cache.put(("k", 1), {"env_ldr": 10})
+    assert len(cache.cache) == 2 and cache.get(("k", 2)) is not None
+    cache.get(("k", 1))
+    cache.put(("k", 3), {"env_ldr": 3})                   # evicts 2 (least recently used), not 1
+    assert cache.get(("k", 2)) is None and cache.get(("k", 1)) == {"env_ldr": 10}
     with pytest.raises(ValueError):
         pe.render_projection_from_panorama(3.14, (8, 8))
     with pytest.raises(ValueError):                                                     # CPU tensor: the device path refuses

@@ -174,3 +174,58 @@ def test_batched_clips_are_rejected_like_the_reference():
         pipe.generate_video({"rgb": clip, "video": clip, "context_index": ci}, seed=3)
     with pytest.raises(ValueError):
         pipe.generate_video({"context_index": ci})                      # no tensor to infer the clip shape from
+
+
+def test_inverse_node_with_batched_passes_equals_the_pass_loop(monkeypatch):
+    """pipeline.batch_passes: the five G-buffer passes as ONE sampler run (generate_video_passes, the passes batched along the
+    token rows of every kernel) must return exactly the frames of the reference's pass-by-pass loop (nodes.py:187-205)"""
+    for name in ("comfy", "comfy.utils", "comfy.model_management", "folder_paths"):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    from drb200 import nodes
+    vae, _ = _vae()
+    pipe, model, _ = _pipeline(MICRO_INVERSE, "inverse", vae, 2)
+    image = torch.rand(1, 9, 32, 48, 3, generator=torch.Generator().manual_seed(9))
+    assert not pipe.wants_batched_passes()                # automatic: only when the net is context-parallel
+    loop = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=0.0, seed=42)
+    pipe.batch_passes, pipe.pass_batch = True, 5
+    batched = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=0.0, seed=42)
+    pipe.pass_batch = 2                                   # 2 + 2 + 1 passes per sampler run
+    chunked = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=0.0, seed=42)
+    for a, b, c in zip(loop, batched, chunked):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    pipe.guidance_saved = pipe.guidance
+    loop_g = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=1.5, seed=7)     # CFG: 10 sequences per step
+    pipe.batch_passes = False
+    ref_g = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=1.5, seed=7)
+    for a, b in zip(loop_g, ref_g):
+        assert torch.equal(a, b)
+
+
+def test_loader_node_to_inverse_pass_on_the_gpu(tmp_path, monkeypatch):
+    """checkpoint files -> LoadDiffusionRendererModel.load_pipeline (meta skeleton, to_empty on the GPU, strict load,
+    nodes.py:94-115) -> Cosmos1InverseRenderer: the same frames as a model that was handed its weights directly"""
+    from drb200 import nodes
+    from drb200.CleanVAE import AutoencoderKLCosmos, CleanVAE
+    from drb200.diffusion_renderer_pipeline import CleanDiffusionRendererPipeline
+    from drb200.model_diffusion_renderer import CleanDiffusionRendererModel
+    from tests.test_loader_cpu import _stub_comfy, write_models
+    from tests.util import model_config
+    sd, vsd = write_models(str(tmp_path), MICRO_INVERSE, True, "inverse.pt")
+    _stub_comfy(monkeypatch, str(tmp_path), DEV)
+    (pipe,) = nodes.LoadDiffusionRendererModel().load_pipeline("inverse.pt")
+    pipe.num_steps = 2
+    image = torch.rand(1, 9, 32, 48, 3, generator=torch.Generator().manual_seed(4))
+    got = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=0.0, seed=11)
+    model = CleanDiffusionRendererModel(model_config(MICRO_INVERSE, "inverse"))
+    model.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    model = model.to(device=DEV, dtype=torch.bfloat16)
+    vm = AutoencoderKLCosmos(encoder_block_out_channels=VDIMS.encoder_block_out_channels, decode_block_out_channels=VDIMS.decode_block_out_channels)
+    vm.load_state_dict(vsd, strict=True)
+    vae = CleanVAE(model=vm)
+    vae.to(DEV)
+    vae.reset_dtype(torch.bfloat16)
+    ref_pipe = CleanDiffusionRendererPipeline(checkpoint_dir="", checkpoint_name="", model_type=None, vae_instance=vae, model_instance=model,
+                                              guidance=0.0, num_steps=2, seed=42)
+    want = nodes.Cosmos1InverseRenderer().run_inverse_pass(ref_pipe, image, guidance=0.0, seed=11)
+    for a, b in zip(got, want):
+        assert torch.isfinite(a).all() and torch.equal(a, b)

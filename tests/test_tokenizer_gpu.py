@@ -281,3 +281,37 @@ def test_chunked_encode_decode_equals_per_window_calls():
         vae.decode_chunked(z[:, :, :4], pixel_chunk_duration=pcd)
     with pytest.raises(ValueError):
         vae.encode_chunked(x, pixel_chunk_duration=16)
+
+
+def test_chunked_per_chunk_latent_normalisation():
+    """opt-in per-chunk mean / std of the upstream chunking tokenizer (pretrained_vae.py:142,150) with the statistics layout
+    of VAE_config.json:21-536 (16 channels x 16 latent frames): bit-equal to the reference's bf16 tensor arithmetic, and
+    decode_chunked(normalize=True) undoes encode_chunked(normalize=True)"""
+    import json
+    import os
+    from drb200.CleanVAE import AutoencoderKLCosmos, CleanVAE
+    cfg_path = os.path.join(os.path.dirname(__file__), "golden", "vae_latent_stats.json")
+    with open(cfg_path) as f:
+        stats = json.load(f)                              # latents_mean / latents_std copied from the reference config
+    assert len(stats["latents_mean"]) == len(stats["latents_std"]) == 256
+    sd = vo.make_vae_state_dict(vo.SMALL_VAE, seed=7)
+    model = AutoencoderKLCosmos(encoder_block_out_channels=vo.SMALL_VAE.encoder_block_out_channels,
+                                decode_block_out_channels=vo.SMALL_VAE.decode_block_out_channels, **stats)
+    model.load_state_dict(sd, strict=True)
+    vae = CleanVAE(model=model)
+    vae.to(DEV)
+    vae.reset_dtype(torch.bfloat16)
+    pcd = 17                                              # 3 latent frames per chunk
+    x = (torch.rand(1, 3, 2 * pcd, 32, 48, device=DEV, generator=gen(33)) * 2 - 1).bfloat16()
+    z_raw = vae.encode_chunked(x, pixel_chunk_duration=pcd)
+    z = vae.encode_chunked(x, pixel_chunk_duration=pcd, normalize=True, max_enc_batch_size=1)
+    mean = torch.tensor(stats["latents_mean"], device=DEV).view(1, 16, -1, 1, 1)[:, :, :3].bfloat16()
+    std = torch.tensor(stats["latents_std"], device=DEV).view(1, 16, -1, 1, 1)[:, :, :3].bfloat16()
+    want = torch.cat([(z_raw[:, :, i * 3:(i + 1) * 3] - mean) / std for i in range(2)], dim=2)     # bf16 tensor ops, as :142
+    assert torch.equal(z, want)
+    back = torch.cat([z[:, :, i * 3:(i + 1) * 3] * std + mean for i in range(2)], dim=2)           # :150
+    y = vae.decode_chunked(z, pixel_chunk_duration=pcd, normalize=True, max_dec_batch_size=1)
+    assert torch.equal(y, vae.decode_chunked(back, pixel_chunk_duration=pcd))
+    plain, _ = _product_vae(vo.SMALL_VAE, seed=7)         # a config without statistics refuses
+    with pytest.raises(ValueError):
+        plain.encode_chunked(x, pixel_chunk_duration=pcd, normalize=True)
