@@ -130,6 +130,7 @@ class AutoencoderKLCosmos(nn.Module):
             self._add_param(key, shape)
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None
+        self.fused_spatial_attention = True    # False: the GEMM -> softmax -> GEMM form also at dim 512 (A/B measurements)
 
     # ---------------------------------------------------------------------------------------------- parameters
     def param_shapes(self) -> Iterator[Tuple[str, Tuple[int, ...]]]:
@@ -277,7 +278,10 @@ class AutoencoderKLCosmos(nn.Module):
         qkv, _ = self._conv(p + ".qkv", h)                                    # [T, H, W, 3C]
         if temporal:
             o = ops.temporal_attention(qkv)
+        elif C == 512 and self.fused_spatial_attention:
+            o = ops.spatial_attention_d512(qkv)                               # one flash kernel, no score matrix (the real net)
         else:
+            # other widths (reduced test nets): scores GEMM -> row softmax -> P.V GEMM per frame
             n = H * W
             ld = (n + 7) // 8 * 8
             o = torch.empty((T, H, W, C), device=x.device, dtype=BF16)

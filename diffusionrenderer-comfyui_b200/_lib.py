@@ -56,6 +56,7 @@ PROTOTYPES = {
     "drb_groupnorm_apply_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p],
     "drb_softmax_rows": [c_void_p, c_int64, c_int, c_int, c_float, c_void_p],
     "drb_transpose_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p],
+    "drb_spatial_attention_d512": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p],
     "drb_temporal_attention_cl": [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p],
     "drb_planar_to_cl": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],
     "drb_cl_to_planar": [c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p],

@@ -39,9 +39,11 @@ constexpr int kABytes = 128 * kBlockK * 2;      // 16 KB
 constexpr int kBBytes = kMaxN * kBlockK * 2;    // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kStages = 4;
-constexpr int kEpiStage = 4 * 2048;             // per epilogue warp: 32 pixels x 64 B (one 32-channel chunk), XOR-swizzled
+constexpr int kEpiWarps = 8;                    // two per TMEM lane quadrant, each taking half of the tile's 32-column chunks
+constexpr int kEpiStage = kEpiWarps * 4096;     // per epilogue warp: 2 x (32 pixels x 64 B = one 32-channel chunk), XOR-swizzled:
+                                                // [0, 2048) output rows on their way out, [2048, 4096) skip-term rows on their way in
 constexpr int kConvSmem = kStages * kStageBytes + 1024 + 256 + kEpiStage;
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 128 + kEpiWarps * 32;
 
 struct ConvMaps {
   CUtensorMap x[4];   // [0] for stride 1; [py*2 + px] parity views for stride 2
@@ -101,7 +103,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);
+      mbar_init(&tmem_empty_bar[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -114,14 +116,22 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // n-tile fastest: the CTAs working on one spatial tile at the same time share its activation boxes in L2
+  // Tile order.  Spatial kernels: n-tile fastest, then w, h, t — the CTAs working on one spatial tile at the same time share
+  // its activation boxes in L2, and neighbouring tiles share their halo.  Temporal kernels (kt > 1): the FRAME runs right
+  // after the n-tile, so the CTAs running concurrently hold the same spatial tile at consecutive frames and the kt source
+  // frames each of them reads are the ones its neighbours read too: every input box comes from HBM once (the spatial
+  // order re-read it kt times: a frame is 29 - 58 MB, and input + output + skip of one output frame overflow the L2).
   auto decode_tile = [&](int tile, int& t, int& h0, int& w0, int& n0) {
     const int tn = tile % tiles_n;
     int m = tile / tiles_n;
+    if (p.kt > 1) {
+      t = m % p.T_out;
+      m /= p.T_out;
+    }
     const int tw = m % tiles_w;
     m /= tiles_w;
     const int th = m % tiles_h;
-    t = m / tiles_h;
+    if (p.kt <= 1) t = m / tiles_h;
     h0 = th * kTileH;
     w0 = tw * kTileW;
     n0 = tn * p.block_n;
@@ -195,20 +205,25 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     }
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp_idx - 4;
+    // Eight warps: warp w reads TMEM lane quadrant w % 4 (its 32 output positions) and takes half of the tile's 32-column
+    // chunks.  With few taps (1x1x1, 3x1x1) a tile's MMAs take 1 - 6 k cycles and the epilogue — bias, skip term, bf16
+    // store, GroupNorm sums — is what bounds the kernel, so (a) it is spread over twice the warps and (b) the skip-term
+    // rows are fetched into registers BEFORE the wait for the accumulator, i.e. under the tile's MMAs.
+    const int q = warp_idx & 3;
+    const int ew = warp_idx - 4;
+    const int nch = (p.block_n + 31) / 32, per = (nch + 1) / 2;
+    const int c_begin = (ew >> 2) * per, c_end = min(nch, c_begin + per);
+    uint8_t* my_stage = epi_stage + ew * 4096;
+    uint8_t* res_stage = my_stage + 2048;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       int t, h0, w0, n0;
       decode_tile(tile, t, h0, w0, n0);
       const int as = iter & 1;
-      mbar_wait(&tmem_full_bar[as], (iter >> 1) & 1);
-      tc_fence_after();
       const int r = q * 32 + lane;
       const int h = h0 + r / kTileW, w = w0 + r % kTileW;
       const bool ok = h < p.H_out && w < p.W_out;
       const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
-      const int64_t pix = (static_cast<int64_t>(t) * p.out_H + oh) * p.out_W + ow;
-      __nv_bfloat16* orow = p.out + pix * p.Cout;
       // residual source rows (up to 4 averaged)
       const __nv_bfloat16* rrow[4] = {nullptr, nullptr, nullptr, nullptr};
       int nres = 0;
@@ -240,12 +255,57 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           rrow[1] = rpix(2 * t, oh, ow);
         }
       }
+      // Single-source skip terms (resnet / attention skip, the "+ x" of the upsamplers) are fetched COALESCED: per 32-channel
+      // chunk the warp reads its 32 pixels x 64 B with 4 lanes per pixel (8 pixels = 8 half-lines per instruction, instead of
+      // 32 lanes on 32 different lines — that form saturated the LSU: ncu lg_throttle, +75 % on the (3,1,1) convolutions),
+      // parks them in shared memory and every thread picks up its own row.  The loads of chunk c + 1 are issued before
+      // chunk c is processed; those of the first chunk before the wait for the accumulator.
+      const bool pre = p.resid_mode == DRB_RES_SAME || p.resid_mode == DRB_RES_FRAME_UP2 || p.resid_mode == DRB_RES_NEAREST_UP_HW;
+      const __nv_bfloat16* rp[4] = {nullptr, nullptr, nullptr, nullptr};
+      if (pre) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r2 = q * 32 + it * 8 + (lane >> 2);
+          const int h2 = h0 + r2 / kTileW, w2 = w0 + r2 % kTileW;
+          if (h2 < p.H_out && w2 < p.W_out) {
+            int tt = t, hh = h2 * p.out_scale + p.out_off_h, ww = w2 * p.out_scale + p.out_off_w;
+            if (p.resid_mode == DRB_RES_FRAME_UP2) tt = (t + 1) >> 1;
+            if (p.resid_mode == DRB_RES_NEAREST_UP_HW) { hh >>= 1; ww >>= 1; }
+            rp[it] = p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout + n0 + (lane & 3) * 8;
+          }
+        }
+      }
+      uint4 rnext[4];
+      auto issue_skip = [&](int c) {
+        const int cl = c * 32 + (lane & 3) * 8;
+        const bool live = c < c_end && cl < p.block_n && n0 + cl < p.Cout;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          rnext[it] = (live && rp[it] != nullptr) ? *reinterpret_cast<const uint4*>(rp[it] + c * 32) : make_uint4(0u, 0u, 0u, 0u);
+      };
+      if (pre) issue_skip(c_begin);
+      mbar_wait(&tmem_full_bar[as], (iter >> 1) & 1);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kMaxN;
       float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < kMaxN / 32; ++c) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = c_begin + ci;
         const int col = n0 + c * 32;
-        if (c * 32 >= p.block_n || col >= p.Cout) break;   // warp-uniform
+        if (c >= c_end || col >= p.Cout) break;   // warp-uniform
+        uint4 rmine[4];
+        if (pre) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int pr = it * 8 + (lane >> 2);
+            *reinterpret_cast<uint4*>(res_stage + pr * 64 + (((lane & 3) ^ ((pr >> 1) & 3)) * 16)) = rnext[it];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            rmine[g] = *reinterpret_cast<const uint4*>(res_stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) * 16));
+          issue_skip(c + 1);              // in flight while this chunk is processed
+        }
         uint32_t acc[32];
         tmem_ld32(taddr + c * 32, acc);
         tmem_wait_ld();
@@ -263,15 +323,25 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           }
           if (nres > 0) {
             float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (i >= nres || rrow[i] == nullptr) continue;
-              const uint4 rv = *reinterpret_cast<const uint4*>(rrow[i] + cg);
+            if (pre) {
+              const uint4 rv = rmine[g];
               const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                ra[2 * j] += bf16_lo(rr[j]);
-                ra[2 * j + 1] += bf16_hi(rr[j]);
+                ra[2 * j] = bf16_lo(rr[j]);
+                ra[2 * j + 1] = bf16_hi(rr[j]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (i >= nres || rrow[i] == nullptr) continue;
+                const uint4 rv = *reinterpret_cast<const uint4*>(rrow[i] + cg);
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  ra[2 * j] += bf16_lo(rr[j]);
+                  ra[2 * j + 1] += bf16_hi(rr[j]);
+                }
               }
             }
             // the reference rounds the convolution output to bf16 before adding the skip term
@@ -286,7 +356,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             s1 += a + b;
             s2 += a * a + b * b;
           }
-          *reinterpret_cast<uint4*>(epi_stage + q * 2048 + lane * 64 + ((g ^ ((lane >> 1) & 3)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         // this warp's 32 pixels are two rows of 16 consecutive pixels: store 64-byte channel segments, 8 pixels per instruction
         __syncwarp();
@@ -297,7 +367,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           if (ph < p.H_out && pw < p.W_out && col + ch * 8 < p.Cout && c * 32 + ch * 8 < p.block_n) {
             const int64_t px = (static_cast<int64_t>(t) * p.out_H + ph * p.out_scale + p.out_off_h) * p.out_W + pw * p.out_scale + p.out_off_w;
             *reinterpret_cast<uint4*>(p.out + px * p.Cout + col + ch * 8) =
-                *reinterpret_cast<const uint4*>(epi_stage + q * 2048 + rr * 64 + ((ch ^ ((rr >> 1) & 3)) * 16));
+                *reinterpret_cast<const uint4*>(my_stage + rr * 64 + ((ch ^ ((rr >> 1) & 3)) * 16));
           }
         }
         __syncwarp();

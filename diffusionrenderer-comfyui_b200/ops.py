@@ -315,6 +315,19 @@ def transpose(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def spatial_attention_d512(qkv: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv [T,H,W,1536] channels-last (q | k | v, one head of dim 512) -> softmax(q k^T / sqrt(512)) v per frame, [T,H,W,512]"""
+    _req_cl(qkv, "qkv")
+    T, H, W, C3 = qkv.shape
+    if C3 != 1536:
+        raise ValueError("the fused spatial attention is specialised for one head of dim 512 (q | k | v = 1536 channels)")
+    if out is None:
+        out = torch.empty((T, H, W, 512), device=qkv.device, dtype=BF16)
+    _req_cl(out, "out")
+    _lib.call("drb_spatial_attention_d512", qkv.data_ptr(), C3, out.data_ptr(), 512, T, H * W, _stream())
+    return out
+
+
 def temporal_attention(qkv: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req_cl(qkv, "qkv")
     T, H, W, C3 = qkv.shape

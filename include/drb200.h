@@ -254,6 +254,11 @@ int drb_groupnorm_apply_cl(const void* x, void* out, const double* stats, const 
 int drb_softmax_rows(void* s, int64_t ld, int rows, int cols, float scale, void* stream);
 /* out[c][r] = in[r][c] for r < rows, 0 for rows <= r < ld_out (V^T as the K-major operand of the P.V GEMM). */
 int drb_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols, void* stream);
+/* The same attention for C = 512 (the CV8x8x8 mid blocks) as ONE flash-attention kernel: qkv bf16 [frames][n][ld >= 1536] laid
+ * out q | k | v (512 columns each), out bf16 [frames][n][ld_o >= 512]; softmax(q k^T / sqrt(512)) v per frame, no score
+ * matrix in memory.  A CTA owns 128 query rows and one 256-column half of v / out (TMEM: two score buffers + the half
+ * accumulator), so q k^T is computed twice: 1.5x the algorithmic MMA work instead of five passes over 2 n^2 bytes. */
+int drb_spatial_attention_d512(const void* qkv, int64_t ld, void* out, int64_t ld_o, int frames, int n, void* stream);
 /* Causal temporal attention (one head of dim C over the T frames of a pixel): qkv bf16 [T][hw][3C] -> out [T][hw][C]. */
 int drb_temporal_attention_cl(const void* qkv, void* out, int T, int64_t hw, int C, void* stream);
 

@@ -315,3 +315,48 @@ def test_chunked_per_chunk_latent_normalisation():
     plain, _ = _product_vae(vo.SMALL_VAE, seed=7)         # a config without statistics refuses
     with pytest.raises(ValueError):
         plain.encode_chunked(x, pixel_chunk_duration=pcd, normalize=True)
+
+
+@pytest.mark.parametrize("T,H,W,gain", [(2, 8, 8, 1.0), (3, 12, 20, 1.0), (1, 44, 80, 1.0), (2, 24, 40, 6.0)])
+def test_fused_spatial_attention_d512(T, H, W, gain):
+    """drb_spatial_attention_d512 (one head of dim 512 over the H*W tokens of a frame, flash form) against fp32 SDPA and
+    against the GEMM -> softmax -> GEMM form it replaces; `gain` 6 gives logits of +-40 whose row maxima keep moving"""
+    import torch.nn.functional as F
+    from drb200 import ops
+    g = gen(41)
+    qkv = torch.randn(T, H, W, 1536, device=DEV, generator=g)
+    qkv[..., :1024] *= gain ** 0.5 * torch.linspace(0.5, 1.5, H * W, device=DEV).reshape(1, H, W, 1)
+    qkv = qkv.bfloat16()
+    out = ops.spatial_attention_d512(qkv)
+    n = H * W
+    flat = qkv.float().reshape(T, n, 1536)
+    ref = F.scaled_dot_product_attention(flat[:, None, :, :512], flat[:, None, :, 512:1024], flat[:, None, :, 1024:])[:, 0]
+    assert out.shape == (T, H, W, 512) and torch.isfinite(out.float()).all()
+    err = rel_l2(out.reshape(T, n, 512), ref)
+    print(f"\nspatial attention {T}x{H}x{W} gain {gain}: rel-L2 vs fp32 SDPA {err:.3e}")
+    assert err <= 5e-3
+    # the unfused form (scores GEMM -> row softmax -> P.V GEMM) rounds the scores to bf16 first: close, not identical
+    ld = (n + 7) // 8 * 8
+    s = torch.empty((n, ld), device=DEV, dtype=torch.bfloat16)
+    vt = torch.empty((512, ld), device=DEV, dtype=torch.bfloat16)
+    rows = qkv.reshape(T * n, 1536)
+    if n % 8 == 0:
+        ops.gemm(rows[:n, :512], rows[:n, 512:1024], out=s)
+        ops.softmax_rows(s, n, 1.0 / 512 ** 0.5)
+        ops.transpose(rows[:n, 1024:], vt)
+        old = ops.gemm(s, vt)
+        assert rel_l2(out.reshape(T, n, 512)[0], old) <= 2e-2 * max(1.0, gain)
+
+
+def test_full_width_tokenizer_with_and_without_the_fused_spatial_attention():
+    """the whole encode with the mid-block attention as one flash kernel vs the GEMM -> softmax -> GEMM form: same result up
+    to the bf16 rounding of the scores the unfused form adds"""
+    vae, sd = _product_vae(vo.FULL_VAE, seed=9)
+    x = (torch.rand(1, 3, 9, 128, 192, device=DEV, generator=gen(44)) * 2 - 1).bfloat16()
+    z = vae.encode(x)
+    vae.model.fused_spatial_attention = False
+    z_unfused = vae.encode(x)
+    vae.model.fused_spatial_attention = True
+    assert torch.isfinite(z.float()).all() and rel_l2(z, z_unfused) <= 1e-2
+    z32 = vo.encode({k: v.bfloat16().float() for k, v in sd.items()}, vo.FULL_VAE, x.float())
+    assert rel_l2(z, z32) <= rel_l2(z_unfused, z32) + 2e-3
