@@ -258,6 +258,8 @@ def attention_traffic(S, heads):
     except Exception as e:
         return None, f"unavailable: {e}", None
     val = rec.get("traffic_bytes", {}).get(f"{S}x{heads}")
+    if val is None and f"{S}x32" in rec.get("traffic_bytes", {}) and rec.get("traffic_bytes_per_head"):
+        val = rec["traffic_bytes_per_head"] * heads      # every (sequence, head) pair moves its own Q, K, V, O once
     if sha != rec.get("attention_cu_sha256"):
         return None, rec.get("source"), True
     return val, rec.get("source"), False

@@ -26,6 +26,8 @@
 // per-frame sum / sum-of-squares of the stored values accumulated for the per-frame GroupNorm that follows.
 //
 // Roofline: tensor pipe, 2 * T*H*W * Cout * taps*Cin flop per launch.
+#include <stdlib.h>
+
 #include "../../include/drb200.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -36,13 +38,20 @@ namespace {
 constexpr int kTileH = 8, kTileW = 16;          // 128 output positions per M tile
 constexpr int kMaxN = 256, kBlockK = 64, kUmmaK = 16;
 constexpr int kABytes = 128 * kBlockK * 2;      // 16 KB
-constexpr int kBBytes = kMaxN * kBlockK * 2;    // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kStages = 4;
+// kCta = 1: one CTA per 128-position tile, W tile of up to 256 rows staged per CTA (48 KB stages, 4 of them).
+// kCta = 2: a CTA pair (cta_group::2 MMA, M = 256 = two position tiles) shares the W tile — each CTA stages half of its rows
+// (32 KB stages, 6 of them).  With few taps the W tile is most of what a k-block pulls from L2, and at full MMA rate 148
+// CTAs x 48 KB per 512 cycles is above the ~6300 B/cycle the L2 delivers chip-wide: the pair form cuts that by a third.
+template <int kCta>
+struct ConvCfg {
+  static constexpr int kBBytes = kMaxN / kCta * kBlockK * 2;   // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;        // 48 KB / 32 KB
+  static constexpr int kStages = kCta == 1 ? 4 : 6;            // 192 KB of operand ring
+};
 constexpr int kEpiWarps = 8;                    // two per TMEM lane quadrant, each taking half of the tile's 32-column chunks
 constexpr int kEpiStage = kEpiWarps * 4096;     // per epilogue warp: 2 x (32 pixels x 64 B = one 32-channel chunk), XOR-swizzled:
                                                 // [0, 2048) output rows on their way out, [2048, 4096) skip-term rows on their way in
-constexpr int kConvSmem = kStages * kStageBytes + 1024 + 256 + kEpiStage;
+constexpr int kConvSmem = 4 * (kABytes + kMaxN * kBlockK * 2) + 1024 + 256 + kEpiStage;   // the same for both flavours
 constexpr int kConvThreads = 128 + kEpiWarps * 32;
 
 struct ConvMaps {
@@ -71,8 +80,10 @@ __device__ __forceinline__ int src_frame(int tmode, int t, int dt, int kt) {
   return max(t + dt - (kt - 1), 0);                                          // causal: first frame replicated in front
 }
 
+template <int kCta>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
+  constexpr int kStages = ConvCfg<kCta>::kStages, kStageBytes = ConvCfg<kCta>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -87,7 +98,10 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   const int tiles_w = (p.W_out + kTileW - 1) / kTileW, tiles_h = (p.H_out + kTileH - 1) / kTileH;
   const int tiles_n = (p.Cout + p.block_n - 1) / p.block_n;
   const int tiles_m = p.T_out * tiles_h * tiles_w;
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_tiles = ((tiles_m + kCta - 1) / kCta) * tiles_n;   // units of work: one position tile (pair: two) x one n-tile
+  const uint32_t cta_rank = kCta == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int unit_id = blockIdx.x / kCta, num_units = gridDim.x / kCta;
   const int cchunks = p.Cin / kBlockK;
   const int taps = p.kt * p.kh * p.kw;
   const int num_kb = taps * cchunks;
@@ -103,16 +117,16 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarps);
+      mbar_init(&tmem_empty_bar[i], kEpiWarps * kCta);   // the epilogue warps of every CTA of the group
     }
     fence_barrier_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc<1>(tmem_slot, 512);
-    tmem_relinquish<1>();
+    tmem_alloc<kCta>(tmem_slot, 512);
+    tmem_relinquish<kCta>();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -121,9 +135,13 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   // after the n-tile, so the CTAs running concurrently hold the same spatial tile at consecutive frames and the kt source
   // frames each of them reads are the ones its neighbours read too: every input box comes from HBM once (the spatial
   // order re-read it kt times: a frame is 29 - 58 MB, and input + output + skip of one output frame overflow the L2).
-  auto decode_tile = [&](int tile, int& t, int& h0, int& w0, int& n0) {
+  // Returns false when this CTA's half of a pair unit lies past the last position tile (odd tile count): it then works on
+  // a copy of the last tile and stores nothing.
+  auto decode_tile = [&](int tile, int& t, int& h0, int& w0, int& n0) -> bool {
     const int tn = tile % tiles_n;
-    int m = tile / tiles_n;
+    int m = (tile / tiles_n) * kCta + static_cast<int>(cta_rank);
+    const bool valid = m < tiles_m;
+    if (!valid) m = tiles_m - 1;
     if (p.kt > 1) {
       t = m % p.T_out;
       m /= p.T_out;
@@ -135,6 +153,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     h0 = th * kTileH;
     w0 = tw * kTileW;
     n0 = tn * p.block_n;
+    return valid;
   };
 
   if (warp_idx == 0) {
@@ -142,8 +161,9 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_tx = kABytes + p.block_n * kBlockK * 2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b_rows = p.block_n / kCta;                               // W rows this CTA stages
+      const uint32_t stage_tx = kABytes + b_rows * kBlockK * 2;
+      for (int tile = unit_id; tile < num_tiles; tile += num_units) {
         int t, h0, w0, n0;
         decode_tile(tile, t, h0, w0, n0);
         for (int tap = 0; tap < taps; ++tap) {
@@ -163,24 +183,32 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           for (int cc = 0; cc < cchunks; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            tma_load_4d(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
-            tma_load_2d(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK, n0);
+            if constexpr (kCta == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+              tma_load_4d(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
+              tma_load_2d(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK, n0);
+            } else {   // both CTAs' bytes are accounted on the leader's barrier
+              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx * 2);
+              tma_load_4d_pair(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
+              tma_load_2d_pair(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK,
+                               n0 + static_cast<int>(cta_rank) * b_rows);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane)
-    const uint32_t idesc = make_idesc_bf16(128, p.block_n);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane; leader CTA only)
+    if (is_leader) {
+    const uint32_t idesc = make_idesc_bf16(128 * kCta, p.block_n);
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const bool issuer = elect_one();
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);
     int stage = 0, iter = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = unit_id; tile < num_tiles; tile += num_units, ++iter) {
       const int as = iter & 1;
       mbar_wait(&tmem_empty_bar[as], ((iter >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -193,15 +221,20 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         if (issuer) {
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_ss<1>(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k),
-                       (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (kb | k) != 0);
-          umma_commit(&empty_bar[stage]);
+            umma_ss<kCta>(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k),
+                          (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k), idesc, (kb | k) != 0);
+          if constexpr (kCta == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_pair(&empty_bar[stage], 0x3);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      if (issuer) umma_commit(&tmem_full_bar[as]);
+      if (issuer) {
+        if constexpr (kCta == 1) umma_commit(&tmem_full_bar[as]);
+        else umma_commit_pair(&tmem_full_bar[as], 0x3);
+      }
       __syncwarp();
+    }
     }
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------------ epilogue
@@ -216,13 +249,13 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     uint8_t* my_stage = epi_stage + ew * 4096;
     uint8_t* res_stage = my_stage + 2048;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = unit_id; tile < num_tiles; tile += num_units, ++iter) {
       int t, h0, w0, n0;
-      decode_tile(tile, t, h0, w0, n0);
+      const bool tile_valid = decode_tile(tile, t, h0, w0, n0);
       const int as = iter & 1;
       const int r = q * 32 + lane;
       const int h = h0 + r / kTileW, w = w0 + r % kTileW;
-      const bool ok = h < p.H_out && w < p.W_out;
+      const bool ok = tile_valid && h < p.H_out && w < p.W_out;
       const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
       // residual source rows (up to 4 averaged)
       const __nv_bfloat16* rrow[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -267,7 +300,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         for (int it = 0; it < 4; ++it) {
           const int r2 = q * 32 + it * 8 + (lane >> 2);
           const int h2 = h0 + r2 / kTileW, w2 = w0 + r2 % kTileW;
-          if (h2 < p.H_out && w2 < p.W_out) {
+          if (tile_valid && h2 < p.H_out && w2 < p.W_out) {
             int tt = t, hh = h2 * p.out_scale + p.out_off_h, ww = w2 * p.out_scale + p.out_off_w;
             if (p.resid_mode == DRB_RES_FRAME_UP2) tt = (t + 1) >> 1;
             if (p.resid_mode == DRB_RES_NEAREST_UP_HW) { hh >>= 1; ww >>= 1; }
@@ -364,7 +397,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         for (int it = 0; it < 4; ++it) {
           const int rr = it * 8 + (lane >> 2), ch = lane & 3;
           const int ph = h0 + (q * 32 + rr) / kTileW, pw = w0 + (q * 32 + rr) % kTileW;
-          if (ph < p.H_out && pw < p.W_out && col + ch * 8 < p.Cout && c * 32 + ch * 8 < p.block_n) {
+          if (tile_valid && ph < p.H_out && pw < p.W_out && col + ch * 8 < p.Cout && c * 32 + ch * 8 < p.block_n) {
             const int64_t px = (static_cast<int64_t>(t) * p.out_H + ph * p.out_scale + p.out_off_h) * p.out_W + pw * p.out_scale + p.out_off_w;
             *reinterpret_cast<uint4*>(p.out + px * p.Cout + col + ch * 8) =
                 *reinterpret_cast<const uint4*>(my_stage + rr * 64 + ((ch ^ ((rr >> 1) & 3)) * 16));
@@ -374,8 +407,11 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-      if (p.stats != nullptr) {
+      if (lane == 0) {
+        if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[as]);
+        else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      }
+      if (p.stats != nullptr && tile_valid) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -391,11 +427,37 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta == 2) cluster_sync(); else __syncthreads();   // no CTA leaves while its peer can still signal into it
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
+    tmem_dealloc<kCta>(tmem_base, 512);
   }
+}
+
+template <int kCta>
+int launch_conv(const ConvMaps& maps, const ConvParams& p, int units, cudaStream_t stream) {
+  auto kernel = conv3d_kernel<kCta>;
+  static DeviceOnce configured;   // per flavour and per device: the attribute belongs to the device's context
+  const int rc = device_once(configured, [&] {
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem), "conv3d_kernel smem");
+  });
+  if (rc) return rc;
+  int groups = num_sms() / kCta;
+  if (groups > units) groups = units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * kCta);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = kConvSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DRB_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, p));
+  return 0;
 }
 
 }  // namespace
@@ -459,13 +521,13 @@ extern "C" int drb_conv3d_cl(const drb_conv3d_args* a, void* stream) {
   }
   const int taps = a->kt * a->kh * a->kw;
   const int block_n = a->Cout <= kMaxN ? a->Cout : kMaxN;
+  const int tiles_m = a->T_out * ((a->H_out + kTileH - 1) / kTileH) * ((a->W_out + kTileW - 1) / kTileW);
+  const int tiles_n = (a->Cout + block_n - 1) / block_n;
+  // the CTA-pair flavour needs two position tiles to pair and a W tile that splits into two UMMA-legal halves
+  static const int pair_ok = [] { const char* e = getenv("DRB_CONV_PAIR"); return e ? atoi(e) : 1; }();   // 0: A/B measurements
+  const int cta = (pair_ok && tiles_m >= 2 && block_n % 32 == 0) ? 2 : 1;
   rc = make_tmap_2d_bf16(&maps.w, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cin, static_cast<uint64_t>(taps) * a->Cin,
-                         block_n, kBlockK);
-  if (rc) return rc;
-  static DeviceOnce configured;   // per device: the attribute belongs to the device's context
-  rc = device_once(configured, [] {
-    return check_cuda(cudaFuncSetAttribute(conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem), "conv3d_kernel smem");
-  });
+                         block_n / cta, kBlockK);
   if (rc) return rc;
   ConvParams p{};
   p.T_out = a->T_out; p.H_out = a->H_out; p.W_out = a->W_out;
@@ -479,11 +541,7 @@ extern "C" int drb_conv3d_cl(const drb_conv3d_args* a, void* stream) {
   p.resid_mode = a->resid_mode;
   p.rH = a->resid_H; p.rW = a->resid_W;
   p.stats = a->stats;
-  const int tiles = a->T_out * ((a->H_out + kTileH - 1) / kTileH) * ((a->W_out + kTileW - 1) / kTileW) *
-                    ((a->Cout + block_n - 1) / block_n);
-  int grid = num_sms();
-  if (grid > tiles) grid = tiles;
-  conv3d_kernel<<<grid, kConvThreads, kConvSmem, static_cast<cudaStream_t>(stream)>>>(maps, p);
-  DRB_CUDA(cudaGetLastError());
-  return 0;
+  const int units = ((tiles_m + cta - 1) / cta) * tiles_n;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return cta == 2 ? launch_conv<2>(maps, p, units, s) : launch_conv<1>(maps, p, units, s);
 }

@@ -37,7 +37,12 @@ def _worker(rank, world, port, ret):
         full = torch.arange(16 * 4 * 3 * 5, dtype=torch.float32).reshape(16, 4, 3, 5)
         t0, t1 = shard_frames(4, rank, world)
         got = gather_frames(full[:, t0:t1].contiguous())
-        ret[rank] = bool(torch.equal(got, full))
+        # N batched passes (N, C, T/P, H, W): the frame axis is third from the right whatever leads it
+        full5 = torch.arange(3 * 16 * 4 * 3 * 5, dtype=torch.float32).reshape(3, 16, 4, 3, 5)
+        got5 = gather_frames(full5[:, :, t0:t1].contiguous())
+        # the work split of the batched pipeline: pass p is decoded by rank p mod P, every pass exactly once
+        owners = [p % world for p in range(5)]
+        ret[rank] = bool(torch.equal(got, full)) and bool(torch.equal(got5, full5)) and sorted(set(owners)) == list(range(world))
     finally:
         dist.destroy_process_group()
 
