@@ -374,8 +374,10 @@ class AutoencoderKLCosmos(nn.Module):
         return torch.stack(outs, dim=0)
 
     @torch.no_grad()
-    def decode_tensor(self, z: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
-        """latent (B, 16, t, h, w), multiplied by `scale` on the way in -> (B, 3, 1 + 8(t-1), 8h, 8w)"""
+    def decode_tensor(self, z: torch.Tensor, scale: float = 1.0, to_u8: bool = False, normalize_normal: bool = False) -> torch.Tensor:
+        """latent (B, 16, t, h, w), multiplied by `scale` on the way in -> (B, 3, 1 + 8(t-1), 8h, 8w); with `to_u8` the
+        last stage stores the post-processed uint8 frames (B, T, H, W, 3) instead (diffusion_renderer_pipeline.py:300-318
+        fused into the inverse-Haar store)"""
         c = self.config
         self._check(z, c.latent_channels, "latent")
         self._ensure_packed()
@@ -392,7 +394,7 @@ class AutoencoderKLCosmos(nn.Module):
                     h, st = self._upsample(f"decoder.up_blocks.{i}.upsamplers.0", h, blk["spatial"], blk["temporal"])
             h = self._norm("decoder.norm_out", h, st, True)
             h, _ = self._conv_projection("decoder.conv_out", h, want_stats=False)
-            outs.append(ops.haar_unpatch(h))
+            outs.append(ops.haar_unpatch_u8(h, normalize_normal) if to_u8 else ops.haar_unpatch(h))
         return torch.stack(outs, dim=0)
 
     # the diffusers call surface the reference wrapper uses (CleanVAE.py:50-51, 59-60)
@@ -472,6 +474,13 @@ class CleanVAE:
     @torch.no_grad()
     def decode_scaled(self, latent_5d: torch.Tensor, scale: float) -> torch.Tensor:
         return self.model.decode_tensor(latent_5d, scale)
+
+    @torch.no_grad()
+    def decode_u8(self, latent_5d: torch.Tensor, scale: float = 1.0, normalize_normal: bool = False) -> torch.Tensor:
+        """decode + the pipeline's uint8 post-process in one go: latent (B,16,t,h,w) -> uint8 (B,T,H,W,3) on the device"""
+        if latent_5d.ndim != 5:
+            raise ValueError(f"CleanVAE expects a 5D latent (B, C, T, H, W), but got {latent_5d.shape}")
+        return self.model.decode_tensor(latent_5d, scale, to_u8=True, normalize_normal=normalize_normal)
 
     # Chunked form for clips longer than one tokenizer window — the behaviour of the upstream chunking tokenizer that the
     # reference carries as (unused) `BasePretrainedVideoTokenizer.encode / .decode` (pretrained_vae.py:389-440): the clip is

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "drb_conv3d_cl": [POINTER(Conv3dArgs), c_void_p],
     "drb_haar_patch": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "drb_haar_unpatch": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "drb_haar_unpatch_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "drb_frame_stats_cl": [c_void_p, c_void_p, c_int, c_int64, c_void_p],
     "drb_groupnorm_apply_cl": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p],
     "drb_softmax_rows": [c_void_p, c_int64, c_int, c_int, c_float, c_void_p],

@@ -8,6 +8,7 @@
 
 #include "../../include/drb200.h"
 #include "common.cuh"
+#include "postprocess.cuh"
 #include "ptx.cuh"
 
 namespace drb {
@@ -320,27 +321,10 @@ postprocess_kernel(const __nv_bfloat16* __restrict__ video, uint8_t* __restrict_
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = __bfloat162float(video[c * n_pix + i]);
-    if (normalize_normal) {
-      // diffusion_renderer_pipeline.py:300-310, every tensor op rounds to bf16
-      const float norm = bf16_round(sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
-      const float den = fmaxf(norm, 1e-12f);
-      float blend = bf16_round(bf16_round(norm - 0.2f) / 0.2f);
-      blend = fminf(fmaxf(blend, 0.f), 1.f);
-      const float inv_blend = bf16_round(1.0f - blend);
+    uint8_t o[3];
+    postprocess_pixel(v, normalize_normal, o);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float vn = bf16_round(v[c] / den);
-        v[c] = bf16_round(bf16_round(vn * blend) + bf16_round(v[c] * inv_blend));
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float u = bf16_round(1.0f + v[c]);
-      u = fminf(fmaxf(u, 0.f), 2.f);
-      u = bf16_round(u * 0.5f);
-      u = bf16_round(u * 255.0f);
-      out[i * 3 + c] = static_cast<uint8_t>(u);   // truncating cast, like Tensor.to(torch.uint8)
-    }
+    for (int c = 0; c < 3; ++c) out[i * 3 + c] = o[c];
   }
 }
 

@@ -11,6 +11,7 @@
 
 #include "../../include/drb200.h"
 #include "common.cuh"
+#include "postprocess.cuh"
 #include "ptx.cuh"
 
 namespace drb {
@@ -115,8 +116,13 @@ haar_patch_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
 }
 
 // in [Tp][Hp][Wp][64*C] -> out [C][T][4Hp][4Wp], T = 4*Tp - 3 (the first 3 reconstructed frames are dropped).
+// kU8 (C == 3): the decode post-process rides on the store — instead of the planar bf16 video the kernel writes the uint8
+// BTHWC frames of diffusion_renderer_pipeline.py:300-318 (same values: the pixel is rounded to bf16 first, as the planar
+// store would), saving the 308 MB write + read of the video tensor per decoded clip.
+template <bool kU8>
 __global__ void __launch_bounds__(kHaarPix)
-haar_unpatch_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int Tp, int Hp, int Wp) {
+haar_unpatch_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ out_u8, int C,
+                    int Tp, int Hp, int Wp, float scale, int normalize_normal) {
   extern __shared__ __align__(16) uint8_t hsm[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(hsm);
   const int CC = 64 * C, pitch = CC + 4;
@@ -133,6 +139,8 @@ haar_unpatch_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restr
   const int wp = wp0 + threadIdx.x;
   if (wp >= Wp) return;
   const __nv_bfloat16* row = tile + threadIdx.x * pitch;
+  // kU8: this thread's reconstructed pixels, [c][it][ih][iw] as bf16, parked in a private row behind the input tiles
+  __nv_bfloat16* stash = tile + kHaarPix * pitch + threadIdx.x * pitch;
   for (int c = 0; c < C; ++c) {
     float v[4][4][4];
 #pragma unroll
@@ -148,8 +156,40 @@ haar_unpatch_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restr
       if (t < 0) continue;
 #pragma unroll
       for (int ih = 0; ih < 4; ++ih) {
-        __nv_bfloat16* dst = out + ((static_cast<int64_t>(c) * T + t) * H + (4 * hp + ih)) * W + 4 * wp;
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v[it][ih][0], v[it][ih][1]), pack_bf16x2(v[it][ih][2], v[it][ih][3]));
+        const uint2 packed = make_uint2(pack_bf16x2(v[it][ih][0], v[it][ih][1]), pack_bf16x2(v[it][ih][2], v[it][ih][3]));
+        if constexpr (kU8) {
+          *reinterpret_cast<uint2*>(stash + c * 64 + (it * 4 + ih) * 4) = packed;
+        } else {
+          __nv_bfloat16* dst = out + ((static_cast<int64_t>(c) * T + t) * H + (4 * hp + ih)) * W + 4 * wp;
+          *reinterpret_cast<uint2*>(dst) = packed;
+        }
+      }
+    }
+  }
+  if constexpr (kU8) {
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const int t = 4 * tp + it - 3;
+      if (t < 0) continue;
+#pragma unroll
+      for (int ih = 0; ih < 4; ++ih) {
+        uint8_t bytes[12];
+#pragma unroll
+        for (int iw = 0; iw < 4; ++iw) {
+          float px[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) px[c] = bf16_round(__bfloat162float(stash[c * 64 + (it * 4 + ih) * 4 + iw]) * scale);
+          uint8_t o[3];
+          postprocess_pixel(px, normalize_normal, o);
+          bytes[iw * 3] = o[0];
+          bytes[iw * 3 + 1] = o[1];
+          bytes[iw * 3 + 2] = o[2];
+        }
+        // 4 pixels x RGB = 12 contiguous bytes of the [T][H][W][3] frame (4-byte aligned: the pixel offset is a multiple of 4)
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out_u8 + ((static_cast<int64_t>(t) * H + (4 * hp + ih)) * W + 4 * wp) * 3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          dst[k] = bytes[4 * k] | (bytes[4 * k + 1] << 8) | (bytes[4 * k + 2] << 16) | (static_cast<uint32_t>(bytes[4 * k + 3]) << 24);
       }
     }
   }
@@ -470,23 +510,47 @@ extern "C" int drb_haar_patch(const void* x, void* out, int C, int T, int H, int
   return 0;
 }
 
-extern "C" int drb_haar_unpatch(const void* in, void* out, int C, int Tp, int Hp, int Wp, void* stream) {
-  DRB_REQUIRE(in && out, "null pointer");
+static int haar_unpatch_launch(const void* in, void* out, void* out_u8, int C, int Tp, int Hp, int Wp, float scale,
+                               int normalize_normal, void* stream) {
+  DRB_REQUIRE(in && (out || out_u8), "null pointer");
   DRB_REQUIRE(C >= 1 && C <= kHaarMaxC, "1..4 output channels");
   DRB_REQUIRE(Tp >= 1 && Hp >= 1 && Wp >= 1 && Hp <= 65535 && Tp <= 65535, "bad dims");
-  DRB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "pointers must be 8-byte aligned");
-  const size_t smem = static_cast<size_t>(kHaarPix) * (64 * C + 4) * 2;
+  DRB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0, "pointers must be 8-byte (uint8 output: 4-byte) aligned");
+  const bool u8 = out_u8 != nullptr;
+  DRB_REQUIRE(!u8 || C == 3, "the fused uint8 post-process needs a 3-channel video");
+  // input tiles, plus (uint8 form) one private row per thread for the reconstructed pixels
+  const size_t smem = static_cast<size_t>(kHaarPix) * (64 * C + 4) * 2 * (u8 ? 2 : 1);
   static drb::DeviceOnce configured;   // per device: the attribute belongs to the device's context
   {
     const int rc = drb::device_once(configured, [] {
-      return drb::check_cuda(cudaFuncSetAttribute(haar_unpatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaarPix * (64 * kHaarMaxC + 4) * 2),
-                             "haar_unpatch_kernel smem");
+      const int bytes = kHaarPix * (64 * kHaarMaxC + 4) * 2;
+      int r = drb::check_cuda(cudaFuncSetAttribute(haar_unpatch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes),
+                              "haar_unpatch_kernel smem");
+      if (r) return r;
+      return drb::check_cuda(cudaFuncSetAttribute(haar_unpatch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * bytes),
+                             "haar_unpatch_kernel<u8> smem");
     });
     if (rc) return rc;
   }
-  haar_unpatch_kernel<<<dim3((Wp + kHaarPix - 1) / kHaarPix, Hp, Tp), kHaarPix, smem, STREAM>>>(CBF(in), BF(out), C, Tp, Hp, Wp);
+  const dim3 grid((Wp + kHaarPix - 1) / kHaarPix, Hp, Tp);
+  if (u8)
+    haar_unpatch_kernel<true><<<grid, kHaarPix, smem, STREAM>>>(CBF(in), nullptr, static_cast<uint8_t*>(out_u8), C, Tp, Hp, Wp, scale,
+                                                                normalize_normal);
+  else
+    haar_unpatch_kernel<false><<<grid, kHaarPix, smem, STREAM>>>(CBF(in), BF(out), nullptr, C, Tp, Hp, Wp, 1.0f, 0);
   DRB_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int drb_haar_unpatch(const void* in, void* out, int C, int Tp, int Hp, int Wp, void* stream) {
+  DRB_REQUIRE(out != nullptr, "null pointer");
+  return haar_unpatch_launch(in, out, nullptr, C, Tp, Hp, Wp, 1.0f, 0, stream);
+}
+
+extern "C" int drb_haar_unpatch_u8(const void* in, void* out_u8, int Tp, int Hp, int Wp, int normalize_normal, void* stream) {
+  DRB_REQUIRE(out_u8 != nullptr, "null pointer");
+  return haar_unpatch_launch(in, nullptr, out_u8, 3, Tp, Hp, Wp, 1.0f, normalize_normal, stream);
 }
 
 static int frame_grid_x(int64_t per_frame, int T) {

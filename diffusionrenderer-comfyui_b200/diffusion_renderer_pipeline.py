@@ -58,6 +58,7 @@ class CleanDiffusionRendererPipeline:
         # token count is small (4+ GPUs: full GEMM waves); with 1-2 GPUs one pass at a time is ~3 % faster under the power
         # cap (alternating attention / GEMM phases), so `auto_pass_batch` picks by the size of the context-parallel group
         self.pass_batch: Optional[int] = None
+        self.fuse_postprocess = True           # uint8 frames straight from the tokenizer's last stage (bit-identical)
 
     def set_model_type(self, model_type: str):
         new = model_type.lower()
@@ -149,9 +150,18 @@ class CleanDiffusionRendererPipeline:
                                                        num_steps=self.num_steps, is_negative_prompt=False, seed=effective_seed)
             if cache_key is not None:
                 self._cond_cache[cache_key] = batch["latent_condition"]
+        return self._decode_frames(model, sample, normalize_normal).cpu().numpy()   # uint8 (B,T,H,W,3); the only host sync of the call
+
+    def _decode_frames(self, model, sample: torch.Tensor, normalize_normal: bool) -> torch.Tensor:
+        """latent -> uint8 (B,T,H,W,3) on the device (reference :296-318).  The B200 tokenizer stores the post-processed
+        frames straight from its last stage (`fuse_postprocess`); otherwise decode, then the post-process kernel."""
+        if self.fuse_postprocess:
+            frames = model.decode_u8(sample, normalize_normal)
+            if frames is not None:
+                return frames
         video = model.decode(sample)                                   # (B,3,T,H,W) in [-1,1]
-        frames = [ops.postprocess_u8(video[b].to(torch.bfloat16).contiguous(), normalize_normal) for b in range(video.shape[0])]
-        return torch.stack(frames, dim=0).cpu().numpy()                # uint8 (B,T,H,W,3); the only host sync of the call
+        return torch.stack([ops.postprocess_u8(video[b].to(torch.bfloat16).contiguous(), normalize_normal)
+                            for b in range(video.shape[0])], dim=0)
 
     def wants_batched_passes(self) -> bool:
         if self.batch_passes is not None:
@@ -191,8 +201,7 @@ class CleanDiffusionRendererPipeline:
         frames = []
         for p, flag in enumerate(flags):
             if world == 1 or p % world == rank:
-                video = model.decode(samples[p:p + 1])                  # (1,3,T,H,W) in [-1,1]
-                frames.append(ops.postprocess_u8(video[0].to(torch.bfloat16).contiguous(), flag))
+                frames.append(self._decode_frames(model, samples[p:p + 1], flag)[0])
             else:
                 frames.append(torch.empty((T, H, W, 3), device=samples.device, dtype=torch.uint8))
         if world > 1:

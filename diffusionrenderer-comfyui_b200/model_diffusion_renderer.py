@@ -140,6 +140,17 @@ class CleanDiffusionRendererModel(nn.Module):
             return self.vae.decode_scaled(x, 1.0 / self.scheduler.sigma_data)
         return self.vae.decode(x / self.scheduler.sigma_data)
 
+    def decode_u8(self, x: Tensor, normalize_normal: bool = False) -> Optional[Tensor]:
+        """decode (:148-156) + the pipeline's post-process (diffusion_renderer_pipeline.py:300-318) as one pass when the
+        tokenizer offers it: uint8 (B,T,H,W,3) on the device, or None (the caller then decodes and post-processes)"""
+        if self.vae is None:
+            raise RuntimeError("VAE not initialized in model.")
+        if x.ndim != 5:
+            raise ValueError(f"Model decode expects a 5D latent (B,C,T,H,W), but got {x.ndim}D.")
+        if not hasattr(self.vae, "decode_u8"):
+            return None
+        return self.vae.decode_u8(x, 1.0 / self.scheduler.sigma_data, normalize_normal)
+
     # ---------------------------------------------------------------- conditions (reference :158-209)
     def prepare_diffusion_renderer_latent_conditions(self, data_batch: Dict[str, Tensor], condition_keys: list = None,
                                                      **kwargs) -> Tensor:

@@ -280,6 +280,17 @@ def haar_unpatch(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
+def haar_unpatch_u8(x: torch.Tensor, normalize_normal: bool = False) -> torch.Tensor:
+    """[Tp,Hp,Wp,192] channels-last -> uint8 [4*Tp-3, 4*Hp, 4*Wp, 3]: inverse Haar + the decode post-process in one kernel"""
+    _req_cl(x, "x")
+    Tp, Hp, Wp, CC = x.shape
+    if CC != 192:
+        raise ValueError("the fused uint8 store needs a 3-channel video (192 wavelet channels)")
+    out = torch.empty((4 * Tp - 3, 4 * Hp, 4 * Wp, 3), device=x.device, dtype=torch.uint8)
+    _lib.call("drb_haar_unpatch_u8", x.data_ptr(), out.data_ptr(), Tp, Hp, Wp, int(bool(normalize_normal)), _stream())
+    return out
+
+
 def frame_stats(x: torch.Tensor) -> torch.Tensor:
     _req_cl(x, "x")
     T = x.shape[0]

@@ -241,6 +241,10 @@ int drb_conv3d_cl(const drb_conv3d_args* args, void* stream);
 int drb_haar_patch(const void* x, void* out, int C, int T, int H, int W, void* stream);
 /* CosmosUnpatcher3d: in bf16 [Tp][Hp][Wp][64*C] -> out bf16 [C][4*Tp-3][4*Hp][4*Wp] (first 3 frames dropped). */
 int drb_haar_unpatch(const void* in, void* out, int C, int Tp, int Hp, int Wp, void* stream);
+/* CosmosUnpatcher3d of a 3-channel video with the decode post-process of diffusion_renderer_pipeline.py:300-318 fused into
+ * its store: in bf16 [Tp][Hp][Wp][192] -> out_u8 uint8 [4*Tp-3][4*Hp][4*Wp][3] = drb_postprocess_u8 of what
+ * drb_haar_unpatch would have written (bit-identical), without the planar bf16 video ever reaching HBM. */
+int drb_haar_unpatch_u8(const void* in, void* out_u8, int Tp, int Hp, int Wp, int normalize_normal, void* stream);
 
 /* CosmosCausalGroupNorm(num_groups = 1) = one (mean, var) per frame over H*W*C, eps 1e-6, affine.
  * drb_frame_stats_cl zeroes and fills stats[T][2] = (sum, sum of squares); drb_conv3d_cl accumulates the same in its

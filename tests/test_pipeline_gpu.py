@@ -193,7 +193,11 @@ def test_inverse_node_with_batched_passes_equals_the_pass_loop(monkeypatch):
     chunked = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=0.0, seed=42)
     for a, b, c in zip(loop, batched, chunked):
         assert torch.equal(a, b) and torch.equal(a, c)
-    pipe.guidance_saved = pipe.guidance
+    pipe.fuse_postprocess = False                         # decode -> planar video -> post-process kernel: the same frames
+    unfused = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=0.0, seed=42)
+    pipe.fuse_postprocess = True
+    for a, b in zip(loop, unfused):
+        assert torch.equal(a, b)
     loop_g = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=1.5, seed=7)     # CFG: 10 sequences per step
     pipe.batch_passes = False
     ref_g = nodes.Cosmos1InverseRenderer().run_inverse_pass(pipe, image, guidance=1.5, seed=7)

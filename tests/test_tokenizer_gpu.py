@@ -360,3 +360,29 @@ def test_full_width_tokenizer_with_and_without_the_fused_spatial_attention():
     assert torch.isfinite(z.float()).all() and rel_l2(z, z_unfused) <= 1e-2
     z32 = vo.encode({k: v.bfloat16().float() for k, v in sd.items()}, vo.FULL_VAE, x.float())
     assert rel_l2(z, z32) <= rel_l2(z_unfused, z32) + 2e-3
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_fused_uint8_store_equals_decode_then_postprocess(normalize):
+    """drb_haar_unpatch_u8 (the post-process of diffusion_renderer_pipeline.py:300-318 fused into the
+    tokenizer's last store) is bit-identical to inverse Haar -> planar bf16 video -> drb_postprocess_u8"""
+    from drb200 import ops
+    g = gen(51)
+    for Tp, Hp, Wp in ((1, 3, 5), (3, 6, 70), (2, 4, 64)):          # ragged blocks of 64 pixels, image path (Tp = 1)
+        x = (torch.randn(Tp, Hp, Wp, 192, device=DEV, generator=g) * 0.35).bfloat16()
+        want = ops.postprocess_u8(ops.haar_unpatch(x), normalize)
+        got = ops.haar_unpatch_u8(x, normalize)
+        assert got.shape == want.shape == (4 * Tp - 3, 4 * Hp, 4 * Wp, 3) and got.dtype == torch.uint8
+        assert torch.equal(got, want)
+        assert got.float().std() > 20                                # real content, both clamps exercised
+    with pytest.raises(ValueError):
+        ops.haar_unpatch_u8(torch.zeros(1, 2, 2, 64, device=DEV, dtype=torch.bfloat16))
+
+
+def test_decode_u8_equals_decode_and_postprocess_end_to_end():
+    from drb200 import ops
+    vae, _ = _product_vae(vo.SMALL_VAE, seed=7)
+    z = torch.randn(1, 16, 3, 4, 6, device=DEV, generator=gen(52)).bfloat16()
+    for flag in (False, True):
+        want = ops.postprocess_u8(vae.decode_scaled(z, 2.0)[0].contiguous(), flag)
+        assert torch.equal(vae.decode_u8(z, 2.0, flag)[0], want)

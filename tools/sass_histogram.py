@@ -43,15 +43,15 @@ def main():
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} (sha256 {sha}...), sm_100a; instruction counts per kernel (static)")
     demangle = subprocess.run(["cu++filt"] + list(kernels), capture_output=True, text=True).stdout.splitlines()
     names = dict(zip(kernels, demangle)) if len(demangle) == len(kernels) else {k: k for k in kernels}
-    print(f"{'kernel':60s} {'total':>7s} " + " ".join(f"{w:>9s}" for w in WATCH))
+    print(f"{'kernel':60s} {'total':>7s} " + " ".join(f"{w:>{max(9, len(w))}s}" for w in WATCH))
     tot = collections.Counter()
     for k, c in kernels.items():
         n = re.sub(r"\(anonymous namespace\)::|drb::", "", names[k])
         n = n[:n.rfind("(")] if "(" in n else n          # drop the parameter list, keep the template arguments
         n = n.replace("(unsigned int)", "").replace("(bool)", "").replace("(int)", "").replace("void ", "").replace("<unnamed>::", "")
-        print(f"{n[:60]:60s} {c['total']:7d} " + " ".join(f"{c.get(w, 0):9d}" for w in WATCH))
+        print(f"{n[:60]:60s} {c['total']:7d} " + " ".join(f"{c.get(w, 0):{max(9, len(w))}d}" for w in WATCH))
         tot.update(c)
-    print(f"{'ALL KERNELS':60s} {tot['total']:7d} " + " ".join(f"{tot.get(w, 0):9d}" for w in WATCH))
+    print(f"{'ALL KERNELS':60s} {tot['total']:7d} " + " ".join(f"{tot.get(w, 0):{max(9, len(w))}d}" for w in WATCH))
     if tot.get("HMMA", 0):
         print("# WARNING: legacy HMMA present", file=sys.stderr)
 
