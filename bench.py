@@ -334,6 +334,7 @@ def time_video(torch, dist, model, wl, rank, world, dev, mode):
     vae = random_tokenizer(torch, dev)
     pipe = CleanDiffusionRendererPipeline(checkpoint_dir="", checkpoint_name="", model_type="inverse", vae_instance=vae,
                                           model_instance=model, guidance=0.0, num_steps=15, seed=42)
+    pipe.pinned_output = True      # as the node classes do: frames land in the pipeline's page-locked staging buffers
     clip = (torch.rand(1, 3, f, hh, ww, generator=torch.Generator().manual_seed(1234)) * 2 - 1).pin_memory()   # host, fp32
     mine = list(range(5)) if mode in ("cp", "ring", "single") else [p for p in range(5) if p % world == rank]
 
@@ -341,12 +342,13 @@ def time_video(torch, dist, model, wl, rank, world, dev, mode):
         pipe.num_steps = steps
         if mode == "cp":
             outs = pipe.generate_video_passes({"rgb": clip, "video": clip}, passes, normalize_normal=[p == 3 for p in passes], seed=42)
-            return [o for o in outs if o is not None]
+            return [o.size for o in outs if o is not None]
         outs = []
         with pipe.shared_conditions():
             for p in passes:
                 batch = {"rgb": clip, "video": clip, "context_index": torch.full((1, 1), p, dtype=torch.long)}
-                outs.append(pipe.generate_video(batch, normalize_normal=(p == 3), seed=42))   # uint8 (1,T,H,W,3) on the host
+                arr = pipe.generate_video(batch, normalize_normal=(p == 3), seed=42)          # uint8 (1,T,H,W,3) on the host
+                outs.append(arr.size)       # (a view of the staging buffer: consumed before the next pass, as the node does)
         return outs
 
     render(mine if mode == "cp" else (mine[:1] or [0]), 1)   # warm-up: allocations, tensor maps, tokenizer weight packing
@@ -360,7 +362,7 @@ def time_video(torch, dist, model, wl, rank, world, dev, mode):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     h2d = clip.numel() * 4 if mine else 0
-    d2h = sum(o.size for o in outs)
+    d2h = sum(outs)
     pipe.vae_instance = None
     model.vae = None
     return dt.item(), len(mine), h2d, d2h
@@ -560,7 +562,8 @@ def run_b200(args, wl):
                          "over the 5 batched passes, decode + post-process of pass p on rank p mod N, host uint8 frames out on rank 0"
                          if mode == "cp" else
                          "CleanDiffusionRendererPipeline.generate_video per G-buffer pass (host fp32 clip in, host uint8 frames out), "
-                         "tokenizer encode once + 15 Euler steps + decode + post-process per pass") + "; random-init tokenizer"}
+                         "tokenizer encode once + 15 Euler steps + decode + post-process per pass") +
+                        "; frames into the pipeline's pinned staging buffers (pinned_output, as the node classes set it); random-init tokenizer"}
 
     # ---- the data-parallel alternative, timed in the same job (N > 1 only): one independent pass per GPU
     dp = None

@@ -59,6 +59,13 @@ class CleanDiffusionRendererPipeline:
         # cap (alternating attention / GEMM phases), so `auto_pass_batch` picks by the size of the context-parallel group
         self.pass_batch: Optional[int] = None
         self.fuse_postprocess = True           # uint8 frames straight from the tokenizer's last stage (bit-identical)
+        # True: the returned arrays are views of page-locked staging buffers owned by the pipeline (D2H of a 154 MB pass:
+        # 2.7 ms instead of 70 ms into pageable memory, tools/video_overhead_probe.py) and stay valid only until the next
+        # generate_video* call on this pipeline.  The node classes switch it on (they convert the frames to float tensors
+        # before returning); plain API users keep the reference's fresh-array contract unless they opt in.
+        self.pinned_output = False
+        self._host_pool: Dict[tuple, list] = {}
+        self._host_next = 0
 
     def set_model_type(self, model_type: str):
         new = model_type.lower()
@@ -150,7 +157,21 @@ class CleanDiffusionRendererPipeline:
                                                        num_steps=self.num_steps, is_negative_prompt=False, seed=effective_seed)
             if cache_key is not None:
                 self._cond_cache[cache_key] = batch["latent_condition"]
-        return self._decode_frames(model, sample, normalize_normal).cpu().numpy()   # uint8 (B,T,H,W,3); the only host sync of the call
+        return self._to_host([self._decode_frames(model, sample, normalize_normal)])[0]   # uint8 (B,T,H,W,3); the only host sync
+
+    def _to_host(self, frames: list) -> list:
+        """device uint8 tensors -> numpy arrays (one synchronisation for all of them)"""
+        if not self.pinned_output:
+            return [f.cpu().numpy() for f in frames]
+        outs = []
+        for i, f in enumerate(frames):
+            pool = self._host_pool.setdefault((tuple(f.shape), f.dtype), [])
+            if i >= len(pool):
+                pool.append(torch.empty(f.shape, dtype=f.dtype).pin_memory())
+            pool[i].copy_(f, non_blocking=True)
+            outs.append(pool[i])
+        torch.cuda.current_stream().synchronize()
+        return [o.numpy() for o in outs]
 
     def _decode_frames(self, model, sample: torch.Tensor, normalize_normal: bool) -> torch.Tensor:
         """latent -> uint8 (B,T,H,W,3) on the device (reference :296-318).  The B200 tokenizer stores the post-processed
@@ -211,7 +232,7 @@ class CleanDiffusionRendererPipeline:
             if self.output_rank is not None and rank != self.output_rank:
                 torch.cuda.current_stream().synchronize()
                 return [None] * len(frames)
-        return [f.unsqueeze(0).cpu().numpy() for f in frames]              # uint8 (1,T,H,W,3) each
+        return self._to_host([f.unsqueeze(0) for f in frames])             # uint8 (1,T,H,W,3) each
 
     def _sample_with_cached_condition(self, model, batch, latent_condition, seed, state_shape):
         with torch.no_grad():

@@ -121,6 +121,7 @@ class Cosmos1InverseRenderer:
         pipeline.set_model_type("inverse")
         pipeline.guidance = guidance
         pipeline.seed = seed
+        pipeline.pinned_output = True          # the frames are converted to float tensors below, before the next call
         clip = _to_5d(image).permute(0, 4, 1, 2, 3) * 2.0 - 1.0          # (B,3,T,H,W) in [-1,1]
         try:
             from comfy.utils import ProgressBar
@@ -188,6 +189,7 @@ class Cosmos1ForwardRenderer:
         pipeline.set_model_type("forward")
         pipeline.guidance = guidance
         pipeline.seed = seed
+        pipeline.pinned_output = True          # the frames are converted to a float tensor below, before the next call
         g5 = {n: _to_5d(t, n) for n, t in (("depth", depth), ("normal", normal), ("roughness", roughness),
                                             ("metallic", metallic), ("base_color", base_color))}
         B, T, H, W, _ = g5["depth"].shape

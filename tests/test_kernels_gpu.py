@@ -331,3 +331,29 @@ def test_fused_qkv_gemm_norm_rope_matches_the_unfused_kernels(M, D, K):
         for sect in range(3):
             assert torch.equal(b[row0:row0 + M, sect * Dp:(sect + 1) * Dp], got[:, sect * D + r * Dp: sect * D + (r + 1) * Dp])
         assert not b[:row0].any() and not b[row0 + M:].any()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_kernels_are_configured_per_device():
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) belongs to a device's context: a process that drives a second GPU
+    must get its kernels configured there too (the round-1 library kept one process-wide flag and failed on device 1)"""
+    from drb200 import ops
+    outs = []
+    for d in (0, 1, 0):
+        with torch.cuda.device(d):
+            dev = f"cuda:{d}"
+            g = torch.Generator(device=dev).manual_seed(1)
+            a = torch.randn(300, 256, device=dev, generator=g).bfloat16()
+            w = torch.randn(512, 256, device=dev, generator=g).bfloat16()
+            qkv = torch.randn(300, 3 * 256, device=dev, generator=g).bfloat16()
+            x = torch.randn(2, 16, 16, 64, device=dev, generator=g).bfloat16()
+            wc = (torch.randn(64, 1, 3, 3, 64, device=dev, generator=g) * 0.05).bfloat16()
+            b = torch.zeros(64, device=dev, dtype=torch.bfloat16)
+            r = (ops.gemm(a, w), ops.attention(qkv[:, :256], qkv[:, 256:512], qkv[:, 512:], 2),
+                 ops.conv3d_cl(x, wc, b, pad_h=1, pad_w=1), ops.haar_unpatch(torch.randn(1, 2, 3, 192, device=dev, generator=g).bfloat16()))
+            torch.cuda.synchronize(d)
+            outs.append([t.cpu() for t in r])
+    for p, q in zip(outs[0], outs[2]):
+        assert torch.equal(p, q)
+    for p, q in zip(outs[0], outs[1]):        # same seeds, same kernels, other device
+        assert torch.equal(p, q)

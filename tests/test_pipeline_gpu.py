@@ -233,3 +233,20 @@ def test_loader_node_to_inverse_pass_on_the_gpu(tmp_path, monkeypatch):
     want = nodes.Cosmos1InverseRenderer().run_inverse_pass(ref_pipe, image, guidance=0.0, seed=11)
     for a, b in zip(got, want):
         assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_pinned_output_returns_the_same_frames():
+    """pipeline.pinned_output: frames arrive in page-locked staging buffers owned by the pipeline (valid until the next
+    call) — same bytes as the fresh-array path"""
+    vae, _ = _vae()
+    pipe, model, _ = _pipeline(MICRO_INVERSE, "inverse", vae, 2)
+    clip = (torch.rand(1, 3, 9, 32, 48, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5)) * 2 - 1)
+    batch = lambda k: {"rgb": clip, "video": clip, "context_index": torch.full((1, 1), k, dtype=torch.long, device=DEV)}
+    fresh = [pipe.generate_video(batch(k), seed=7).copy() for k in (0, 3)]
+    pipe.pinned_output = True
+    a = pipe.generate_video(batch(0), seed=7)
+    assert np.array_equal(a, fresh[0])
+    b = pipe.generate_video(batch(3), seed=7)          # reuses the staging buffer: `a` now shows pass 3
+    assert np.array_equal(b, fresh[1]) and np.shares_memory(a, b)
+    outs = pipe.generate_video_passes({"rgb": clip, "video": clip}, [0, 3], seed=7)
+    assert np.array_equal(outs[0], fresh[0]) and np.array_equal(outs[1], fresh[1]) and not np.shares_memory(outs[0], outs[1])
