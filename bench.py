@@ -623,6 +623,7 @@ def run_b200(args, wl):
         if mode == "cp":
             line["ms_per_iteration"] = ms_max / args.steps
             line["passes_per_iteration"] = batch
+            line["step_equivalents_timed"] = args.steps * batch      # K timed iterations x `batch` passes each; ms_per_step is per step-equivalent
             line["cp_gate"] = gate
         if dp is not None:
             line["dp"] = dp
