@@ -136,10 +136,6 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], uint64_t 
   }
 }
 
-template <int kRegs>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 // UMMA shared-memory descriptors are built as {hi: constant per layout, lo: (address >> 4) | LBO field}, so the issue
 // loop only does 32-bit adds.  K-major 128 x 128 bf16 tile = two 128-row x 128-byte swizzled boxes; k-step `k` covers

@@ -156,6 +156,11 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     return valid;
   };
 
+  // The eight epilogue warps are what bounds the few-tap convolutions, and at the 168 registers a 384-thread CTA allows
+  // the compiler spilled the TMEM address and re-derived shared-memory addresses from SR_TID in every chunk (ncu:
+  // long-scoreboard stalls on LDL / S2R).  Warps 0-3 (one TMA thread, one MMA thread, two idle) hand their registers over.
+  if (warp_idx < 4) {
+  reg_dec<72>();
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -236,7 +241,9 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       __syncwarp();
     }
     }
-  } else if (warp_idx >= 4) {
+  }
+  } else {
+    reg_inc<208>();
     // ------------------------------------------------------------------ epilogue
     // Eight warps: warp w reads TMEM lane quadrant w % 4 (its 32 output positions) and takes half of the tile's 32-column
     // chunks.  With few taps (1x1x1, 3x1x1) a tile's MMAs take 1 - 6 k cycles and the epilogue — bias, skip term, bf16
@@ -321,6 +328,10 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kMaxN;
       float s1 = 0.f, s2 = 0.f;
+      // the chunks are software-pipelined: while chunk c is processed, the accumulator columns of chunk c + 1 are already on
+      // their way out of tensor memory (two register buffers, statically indexed through the full unroll)
+      uint32_t accbuf[2][32];
+      if (c_begin < c_end && n0 + c_begin * 32 < p.Cout) tmem_ld32(taddr + c_begin * 32, accbuf[0]);
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c = c_begin + ci;
@@ -339,22 +350,30 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             rmine[g] = *reinterpret_cast<const uint4*>(res_stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) * 16));
           issue_skip(c + 1);              // in flight while this chunk is processed
         }
-        uint32_t acc[32];
-        tmem_ld32(taddr + c * 32, acc);
+        // bias of this chunk: requested before the wait for the accumulator columns
+        uint4 bias4[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          bias4[g] = (col + g * 8 < p.Cout) ? __ldg(reinterpret_cast<const uint4*>(p.bias + col + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
         tmem_wait_ld();
+        uint32_t (&acc)[32] = accbuf[ci & 1];
+        if (c + 1 < c_end && col + 32 < p.Cout) tmem_ld32(taddr + (c + 1) * 32, accbuf[(ci + 1) & 1]);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          // Straight-line on purpose: lanes without a pixel (ragged tiles) and column groups past Cout compute on finite
+          // dummies and are masked out of the GroupNorm sums / never stored, so the four groups of a chunk interleave
+          // instead of being four divergence-guarded blocks (the epilogue ran at 6.8 cycles per instruction, ncu).
           const int cg = col + g * 8;
-          if (!ok || cg >= p.Cout || c * 32 + g * 8 >= p.block_n) continue;   // (all lanes meet again at the __syncwarp below)
+          const float live = (ok && cg < p.Cout && c * 32 + g * 8 < p.block_n) ? 1.0f : 0.0f;
           float v[8];
-          const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + cg));
+          const uint4 bv = bias4[g];
           const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             v[2 * j] = __uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bb[j]);
             v[2 * j + 1] = __uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bb[j]);
           }
-          if (nres > 0) {
+          if (p.resid_mode != DRB_RES_NONE) {       // uniform
             float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (pre) {
               const uint4 rv = rmine[g];
@@ -364,7 +383,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
                 ra[2 * j] = bf16_lo(rr[j]);
                 ra[2 * j + 1] = bf16_hi(rr[j]);
               }
-            } else {
+            } else if (live != 0.0f) {              // pooled skip terms (two resampling convolutions per net): per-lane sources
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 if (i >= nres || rrow[i] == nullptr) continue;
@@ -386,8 +405,8 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           for (int j = 0; j < 4; ++j) {
             o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
-            s1 += a + b;
-            s2 += a * a + b * b;
+            s1 = fmaf(live, a + b, s1);
+            s2 = fmaf(live * a, a, fmaf(live * b, b, s2));
           }
           *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
