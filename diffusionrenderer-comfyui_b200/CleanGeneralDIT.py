@@ -374,7 +374,7 @@ class CleanGeneralDIT(nn.Module):
                 ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Hh, out=ws["attn"][b * S:(b + 1) * S], max_abs_logit=bound)
         elif cp.mode == "ring":
             for b in range(B):          # the ring schedule runs per sequence (staging buffers and running state are reused)
-                self._ring_attention(ws, b)
+                self._ring_attention(ws, b, bound)
         else:
             # (sequence, local head) pairs are the attention problems of this rank: B * H/P "heads" over all S tokens
             Hp, a2a = Hh // cp.world, ws["a2a"]
@@ -385,7 +385,7 @@ class CleanGeneralDIT(nn.Module):
             ev[1].record()
             timers.append(ev)
 
-    def _ring_attention(self, ws, b: int = 0) -> None:
+    def _ring_attention(self, ws, b: int = 0, bound: Optional[torch.Tensor] = None) -> None:
         """Ring schedule over peer memory for sequence b: block s of rank r is the K/V of rank (r - s) mod P.  While block s
         is attended to on the current stream, block s + 1 is pulled from its owner's [q | k | v] buffer (k | v columns only)
         into the other staging buffer on the copy stream; the attention kernel's ring epilogue merges the blocks."""
@@ -411,7 +411,7 @@ class CleanGeneralDIT(nn.Module):
             if s > 0:
                 main.wait_event(copied[s])
             ops.attention_ring_block(q, kv[:, D:2 * D], kv[:, 2 * D:], Hh, ws["ring_o"], ws["ring_ml"], first=(s == 0),
-                                     last=(s == P - 1), out=ws["attn"][rows])
+                                     last=(s == P - 1), out=ws["attn"][rows], max_abs_logit=bound)
             freed[s] = torch.cuda.Event()
             freed[s].record(main)
 

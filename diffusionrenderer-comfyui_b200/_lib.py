@@ -67,6 +67,8 @@ PROTOTYPES = {
     "drb_envmap_tonemap": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "drb_attention_bf16_ring": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p],
+    "drb_attention_bf16_ring_bounded": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p, c_void_p],
     "drb_gemm_qkv_norm_rope": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, POINTER(c_void_p), c_int, c_int64, c_int, c_void_p],
     "drb_gemm_qkv_norm_rope_batched": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,

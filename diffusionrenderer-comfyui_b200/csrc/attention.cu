@@ -711,6 +711,13 @@ extern "C" int drb_attention_bf16_cp_batched(const void* q, const void* k, const
 extern "C" int drb_attention_bf16_ring(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                                        float* state_o, float* state_ml, int q_len, int kv_len, int num_heads, int first, int last,
                                        void* stream) {
+  return drb_attention_bf16_ring_bounded(q, k, v, ld_qkv, o, ld_o, state_o, state_ml, q_len, kv_len, num_heads, first, last, nullptr,
+                                         stream);
+}
+
+extern "C" int drb_attention_bf16_ring_bounded(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                                               float* state_o, float* state_ml, int q_len, int kv_len, int num_heads, int first,
+                                               int last, const float* max_abs_logit, void* stream) {
   using namespace drb;
   DRB_REQUIRE(state_o && state_ml, "ring attention needs the running-state buffers");
   DRB_REQUIRE((reinterpret_cast<uintptr_t>(state_o) & 15) == 0 && (reinterpret_cast<uintptr_t>(state_ml) & 7) == 0, "state buffers misaligned");
@@ -721,6 +728,7 @@ extern "C" int drb_attention_bf16_ring(const void* q, const void* k, const void*
   ex.ring_ml = state_ml;
   ex.ring_first = first ? 1 : 0;
   ex.ring_last = last ? 1 : 0;
+  ex.logit_bound = max_abs_logit;
   return attention_launch(q, k, v, ld_qkv, peers, 1, o ? ld_o : static_cast<int64_t>(num_heads) * kHeadDim, q_len, kv_len, num_heads,
                           0x7fffffff, 0, stream, ex);
 }

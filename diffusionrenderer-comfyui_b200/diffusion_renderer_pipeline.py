@@ -165,7 +165,10 @@ class CleanDiffusionRendererPipeline:
             return [f.cpu().numpy() for f in frames]
         outs = []
         for i, f in enumerate(frames):
-            pool = self._host_pool.setdefault((tuple(f.shape), f.dtype), [])
+            key = (tuple(f.shape), f.dtype)
+            if key not in self._host_pool:          # another clip size: let the old staging buffers go
+                self._host_pool = {key: []}
+            pool = self._host_pool[key]
             if i >= len(pool):
                 pool.append(torch.empty(f.shape, dtype=f.dtype).pin_memory())
             pool[i].copy_(f, non_blocking=True)

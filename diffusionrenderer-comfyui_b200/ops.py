@@ -473,7 +473,8 @@ def qkv_gemm_norm_rope(a: torch.Tensor, w: torch.Tensor, wq: torch.Tensor, wk: t
 
 
 def attention_ring_block(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, state_o: torch.Tensor,
-                         state_ml: torch.Tensor, first: bool, last: bool, out: Optional[torch.Tensor] = None) -> None:
+                         state_ml: torch.Tensor, first: bool, last: bool, out: Optional[torch.Tensor] = None,
+                         max_abs_logit: Optional[torch.Tensor] = None) -> None:
     """one K/V block of ring attention: merges softmax(q k^T) v over this block into the fp32 running state; the last block
     writes the normalised rows to `out` [q_len, H*128]"""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -488,6 +489,6 @@ def attention_ring_block(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_
         if out is None:
             raise ValueError("the last block needs `out`")
         _req(out, "out")
-    _lib.call("drb_attention_bf16_ring", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _ptr(out) if last else None,
+    _lib.call("drb_attention_bf16_ring_bounded", q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, _ptr(out) if last else None,
               _rows2d(out, "out") if last else 0, state_o.data_ptr(), state_ml.data_ptr(), q.shape[0], k.shape[0], num_heads,
-              int(first), int(last), _stream())
+              int(first), int(last), _bound_ptr(max_abs_logit), _stream())

@@ -80,6 +80,10 @@ int drb_gemm_bf16_sync(const void* A, int64_t lda, const void* W, int64_t ldw, v
  * normalised bf16 rows to o [q_len, ld_o] instead of the state.  Same kernel, other epilogue. */
 int drb_attention_bf16_ring(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o, float* state_o,
                             float* state_ml, int q_len, int kv_len, int num_heads, int first, int last, void* stream);
+/* The same with the logit-bound certificate of drb_attention_bf16_bounded (device float, nullable). */
+int drb_attention_bf16_ring_bounded(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                                    float* state_o, float* state_ml, int q_len, int kv_len, int num_heads, int first, int last,
+                                    const float* max_abs_logit, void* stream);
 
 /* Fused QKV projection: [q | k | v] = A[M,K] @ W[3D,K]^T with, in the epilogue, per-head RMSNorm of q and k (weights
  * wq, wk [128], eps 1e-6) and RoPE from the bf16 tables cos_tab / sin_tab [M,128] — i.e. drb_gemm_bf16 followed by
