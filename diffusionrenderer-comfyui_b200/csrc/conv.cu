@@ -40,19 +40,27 @@ constexpr int kMaxN = 256, kBlockK = 64, kUmmaK = 16;
 constexpr int kABytes = 128 * kBlockK * 2;      // 16 KB
 // kCta = 1: one CTA per 128-position tile, W tile of up to 256 rows staged per CTA (48 KB stages, 4 of them).
 // kCta = 2: a CTA pair (cta_group::2 MMA, M = 256 = two position tiles) shares the W tile — each CTA stages half of its rows
-// (32 KB stages, 6 of them).  With few taps the W tile is most of what a k-block pulls from L2, and at full MMA rate 148
-// CTAs x 48 KB per 512 cycles is above the ~6300 B/cycle the L2 delivers chip-wide: the pair form cuts that by a third.
-template <int kCta>
+// (32 KB stages, 6 of them): a third less operand traffic per MMA, which is what lifted the (1,3,3) convolutions from
+// 1370 - 1460 to 1530 - 1590 TFLOP/s (tensor pipe 96.8 % active).
+// kSplit (pair flavour only, chosen for convolutions with few taps): the epilogue is TWO stages on different warps — four
+// "drain" warps move the accumulator (+ bias, rounded to bf16) from tensor memory into one of two 64 KB tile buffers in
+// shared memory, eight "finish" warps stream the buffer out (skip term, GroupNorm sums, fully coalesced 16-byte loads and
+// stores) — because with 1 - 6 k MMA cycles per tile the single-stage epilogue (10 - 13 k cycles of a latency-bound
+// TMEM -> registers -> shared -> global chain on two warps per scheduler) bounded those kernels.  3-stage operand ring
+// (half-tile buffers with a 5-stage ring measured slower on everything but the plain 512-channel (3,1,1) convolution).
+template <int kCta, bool kSplit>
 struct ConvCfg {
   static constexpr int kBBytes = kMaxN / kCta * kBlockK * 2;   // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;        // 48 KB / 32 KB
-  static constexpr int kStages = kCta == 1 ? 4 : 6;            // 192 KB of operand ring
+  static constexpr int kStages = kSplit ? 3 : (kCta == 1 ? 4 : 6);
+  static constexpr int kThreads = kSplit ? 512 : 384;
 };
-constexpr int kEpiWarps = 8;                    // two per TMEM lane quadrant, each taking half of the tile's 32-column chunks
+constexpr int kEpiWarps = 8;                    // single-stage epilogue: two per TMEM lane quadrant, each taking half of the tile's chunks
 constexpr int kEpiStage = kEpiWarps * 4096;     // per epilogue warp: 2 x (32 pixels x 64 B = one 32-channel chunk), XOR-swizzled:
                                                 // [0, 2048) output rows on their way out, [2048, 4096) skip-term rows on their way in
-constexpr int kConvSmem = 4 * (kABytes + kMaxN * kBlockK * 2) + 1024 + 256 + kEpiStage;   // the same for both flavours
-constexpr int kConvThreads = 128 + kEpiWarps * 32;
+constexpr int kTileBufBytes = 128 * 512;        // split epilogue: 128 positions x 256 channels bf16, 16-byte slots XOR-swizzled by row
+constexpr int kConvSmem = 4 * (kABytes + kMaxN * kBlockK * 2) + 1024 + 256 + kEpiStage;   // the same for all flavours
+static_assert(3 * (kABytes + kMaxN / 2 * kBlockK * 2) + 256 + 2 * kTileBufBytes + 1024 <= kConvSmem, "split flavour must fit");
 
 struct ConvMaps {
   CUtensorMap x[4];   // [0] for stride 1; [py*2 + px] parity views for stride 2
@@ -80,18 +88,20 @@ __device__ __forceinline__ int src_frame(int tmode, int t, int dt, int kt) {
   return max(t + dt - (kt - 1), 0);                                          // causal: first frame replicated in front
 }
 
-template <int kCta>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int kCta, bool kSplit>
+__global__ void __launch_bounds__((ConvCfg<kCta, kSplit>::kThreads), 1)
 conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
-  constexpr int kStages = ConvCfg<kCta>::kStages, kStageBytes = ConvCfg<kCta>::kStageBytes;
+  constexpr int kStages = ConvCfg<kCta, kSplit>::kStages, kStageBytes = ConvCfg<kCta, kSplit>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint8_t* epi_stage = smem + kStages * kStageBytes + 256;
+  uint64_t* buf_full = tmem_empty_bar + 2;     // split epilogue: tile buffer b holds a drained tile / is free again
+  uint64_t* buf_empty = buf_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_empty + 2);
+  uint8_t* epi_stage = smem + kStages * kStageBytes + 256;   // single-stage epilogue staging, or the two tile buffers
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,7 +127,9 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarps * kCta);   // the epilogue warps of every CTA of the group
+      mbar_init(&tmem_empty_bar[i], (kSplit ? 4 : kEpiWarps) * kCta);   // the TMEM-reading warps of every CTA of the group
+      mbar_init(&buf_full[i], 4);                                       // the four drain warps
+      mbar_init(&buf_empty[i], 8);                                      // the eight finish warps
     }
     fence_barrier_init();
   }
@@ -160,7 +172,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   // the compiler spilled the TMEM address and re-derived shared-memory addresses from SR_TID in every chunk (ncu:
   // long-scoreboard stalls on LDL / S2R).  Warps 0-3 (one TMA thread, one MMA thread, two idle) hand their registers over.
   if (warp_idx < 4) {
-  reg_dec<72>();
+  reg_dec<kSplit ? 56 : 72>();
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -242,6 +254,165 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     }
     }
   }
+  } else if (kSplit && warp_idx < 8) {
+    // ------------------------------------------------------------------ split epilogue, stage 1: drain (one warp per TMEM lane quadrant)
+    reg_inc<160>();
+    const int q = warp_idx & 3;
+    const int r = q * 32 + lane;
+    const int nch = (p.block_n + 31) / 32;
+    int iter = 0;
+    for (int tile = unit_id; tile < num_tiles; tile += num_units, ++iter) {
+      int t, h0, w0, n0;
+      decode_tile(tile, t, h0, w0, n0);
+      const int as = iter & 1;
+      mbar_wait(&buf_empty[as], ((iter >> 1) & 1) ^ 1);
+      mbar_wait(&tmem_full_bar[as], (iter >> 1) & 1);
+      tc_fence_after();
+      uint8_t* row_buf = epi_stage + as * kTileBufBytes + r * 512;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kMaxN;
+      uint32_t accbuf[2][32];
+      tmem_ld32(taddr, accbuf[0]);
+#pragma unroll
+      for (int c = 0; c < kMaxN / 32; ++c) {
+        if (c >= nch) break;   // warp-uniform
+        uint4 bias4[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cg = n0 + c * 32 + g * 8;
+          bias4[g] = cg < p.Cout ? __ldg(reinterpret_cast<const uint4*>(p.bias + cg)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        tmem_wait_ld();
+        uint32_t (&acc)[32] = accbuf[c & 1];
+        if (c + 1 < nch) tmem_ld32(taddr + (c + 1) * 32, accbuf[(c + 1) & 1]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t bb[4] = {bias4[g].x, bias4[g].y, bias4[g].z, bias4[g].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = pack_bf16x2(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bb[j]), __uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bb[j]));
+          *reinterpret_cast<uint4*>(row_buf + (((c * 4 + g) ^ (r & 31)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[as]);
+        else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+        mbar_arrive(&buf_full[as]);
+      }
+    }
+  } else if (kSplit) {
+    // ------------------------------------------------------------------ split epilogue, stage 2: finish (eight warps, streaming)
+    // Thread f takes the 16-byte vectors f, f + 256, ... of the tile (row-major, block_n / 8 vectors per position): a warp
+    // reads and writes whole 512-byte channel rows — skip term in, output out — instead of a row per thread.
+    reg_dec<104>();
+    const int f = threadIdx.x - 256;
+    const int vpr = p.block_n >> 3, nvec = 128 * vpr;
+    const bool single = p.resid_mode == DRB_RES_SAME || p.resid_mode == DRB_RES_FRAME_UP2 || p.resid_mode == DRB_RES_NEAREST_UP_HW;
+    int iter = 0;
+    for (int tile = unit_id; tile < num_tiles; tile += num_units, ++iter) {
+      int t, h0, w0, n0;
+      const bool tile_valid = decode_tile(tile, t, h0, w0, n0);
+      const int as = iter & 1;
+      const uint8_t* buf = epi_stage + as * kTileBufBytes;
+      float s1 = 0.f, s2 = 0.f;
+      bool waited = false;
+      for (int k0 = 0; k0 * 256 < nvec; k0 += 4) {
+        int rowv[4], slotv[4];
+        bool okv[4];
+        __nv_bfloat16* outp[4];
+        uint4 skipv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = (k0 + u) * 256 + f;
+          const int row = i / vpr, slot = i - row * vpr;
+          const int h = h0 + row / kTileW, w = w0 + row % kTileW;
+          rowv[u] = row;
+          slotv[u] = slot;
+          okv[u] = tile_valid && i < nvec && h < p.H_out && w < p.W_out && n0 + slot * 8 < p.Cout;
+          const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
+          outp[u] = p.out + ((static_cast<int64_t>(t) * p.out_H + oh) * p.out_W + ow) * p.Cout + n0 + slot * 8;
+          skipv[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (single && okv[u]) {       // the skip rows are requested before the wait for the drained tile
+            int tt = t, hh = oh, ww = ow;
+            if (p.resid_mode == DRB_RES_FRAME_UP2) tt = (t + 1) >> 1;
+            if (p.resid_mode == DRB_RES_NEAREST_UP_HW) { hh >>= 1; ww >>= 1; }
+            skipv[u] = *reinterpret_cast<const uint4*>(p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout + n0 + slot * 8);
+          }
+        }
+        if (!waited) {
+          mbar_wait(&buf_full[as], (iter >> 1) & 1);
+          waited = true;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if ((k0 + u) * 256 + f >= nvec) continue;
+          const uint4 xv = *reinterpret_cast<const uint4*>(buf + rowv[u] * 512 + ((slotv[u] ^ (rowv[u] & 31)) * 16));
+          uint32_t o[4] = {xv.x, xv.y, xv.z, xv.w};
+          if (p.resid_mode != DRB_RES_NONE) {       // uniform
+            float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float rscale = 1.0f;
+            if (single) {
+              const uint32_t rr[4] = {skipv[u].x, skipv[u].y, skipv[u].z, skipv[u].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ra[2 * j] = bf16_lo(rr[j]);
+                ra[2 * j + 1] = bf16_hi(rr[j]);
+              }
+            } else if (okv[u]) {                    // pooled skip terms: 2 or 4 source rows averaged
+              const int row = rowv[u];
+              const int oh = (h0 + row / kTileW) * p.out_scale + p.out_off_h, ow = (w0 + row % kTileW) * p.out_scale + p.out_off_w;
+              const int nsrc = p.resid_mode == DRB_RES_POOL_HW ? 4 : 2;
+              rscale = p.resid_mode == DRB_RES_POOL_HW ? 0.25f : 0.5f;
+              for (int i2 = 0; i2 < nsrc; ++i2) {
+                int tt = t, hh = oh, ww = ow;
+                if (p.resid_mode == DRB_RES_POOL_HW) {
+                  hh = 2 * oh + (i2 >> 1);
+                  ww = 2 * ow + (i2 & 1);
+                  if (hh >= p.rH || ww >= p.rW) continue;
+                } else {
+                  tt = i2 == 0 ? max(2 * t - 1, 0) : 2 * t;
+                }
+                const uint4 rv = *reinterpret_cast<const uint4*>(p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout + n0 + slotv[u] * 8);
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  ra[2 * j] += bf16_lo(rr[j]);
+                  ra[2 * j + 1] += bf16_hi(rr[j]);
+                }
+              }
+            }
+            // the drained value is the convolution output already rounded to bf16, as the reference has it before the add
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = pack_bf16x2(bf16_lo(o[j]) + bf16_round(ra[2 * j] * rscale), bf16_hi(o[j]) + bf16_round(ra[2 * j + 1] * rscale));
+          }
+          if (okv[u]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
+              s1 += a + b;
+              s2 = fmaf(a, a, fmaf(b, b, s2));
+            }
+            *reinterpret_cast<uint4*>(outp[u]) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&buf_empty[as]);
+      if (p.stats != nullptr && tile_valid) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+          atomicAdd(&p.stats[2 * t], static_cast<double>(s1));
+          atomicAdd(&p.stats[2 * t + 1], static_cast<double>(s2));
+        }
+      }
+    }
   } else {
     reg_inc<208>();
     // ------------------------------------------------------------------ epilogue
@@ -453,9 +624,9 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   }
 }
 
-template <int kCta>
+template <int kCta, bool kSplit>
 int launch_conv(const ConvMaps& maps, const ConvParams& p, int units, cudaStream_t stream) {
-  auto kernel = conv3d_kernel<kCta>;
+  auto kernel = conv3d_kernel<kCta, kSplit>;
   static DeviceOnce configured;   // per flavour and per device: the attribute belongs to the device's context
   const int rc = device_once(configured, [&] {
     return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem), "conv3d_kernel smem");
@@ -465,7 +636,7 @@ int launch_conv(const ConvMaps& maps, const ConvParams& p, int units, cudaStream
   if (groups > units) groups = units;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * kCta);
-  cfg.blockDim = dim3(kConvThreads);
+  cfg.blockDim = dim3(ConvCfg<kCta, kSplit>::kThreads);
   cfg.dynamicSmemBytes = kConvSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -562,5 +733,13 @@ extern "C" int drb_conv3d_cl(const drb_conv3d_args* a, void* stream) {
   p.stats = a->stats;
   const int units = ((tiles_m + cta - 1) / cta) * tiles_n;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return cta == 2 ? launch_conv<2>(maps, p, units, s) : launch_conv<1>(maps, p, units, s);
+  // The split, two-stage epilogue pays where the single-stage one bounds the kernel: up to 12 k-blocks per tile (1x1x1,
+  // 3x1x1 at <= 256 channels), or up to 24 when a skip term doubles the epilogue's memory work (tools/conv_t_probe.py:
+  // (3,1,1) 256 -> 256 with skip 0.57 -> 0.44 ms, 512 -> 512 with skip 0.187 -> 0.162; plain 512 -> 512 is better off with
+  // the deeper operand ring of the single-stage flavour, 0.130 vs 0.144).
+  static const int split_ok = [] { const char* e = getenv("DRB_CONV_SPLIT"); return e ? atoi(e) : 1; }();   // 0: A/B measurements
+  const int num_kb = taps * (a->Cin / kBlockK);
+  const bool split = cta == 2 && split_ok && (num_kb <= 12 || (num_kb <= 24 && a->resid != nullptr));
+  if (split) return launch_conv<2, true>(maps, p, units, s);
+  return cta == 2 ? launch_conv<2, false>(maps, p, units, s) : launch_conv<1, false>(maps, p, units, s);
 }
