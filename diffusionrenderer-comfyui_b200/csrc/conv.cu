@@ -305,113 +305,171 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   } else if (kSplit) {
     // ------------------------------------------------------------------ split epilogue, stage 2: finish (eight warps, streaming)
     // Thread f takes the 16-byte vectors f, f + 256, ... of the tile (row-major, block_n / 8 vectors per position): a warp
-    // reads and writes whole 512-byte channel rows — skip term in, output out — instead of a row per thread.
-    reg_dec<104>();
+    // reads and writes whole channel rows — skip term in, output out — instead of a row per thread.  This stage bounds the
+    // few-tap convolutions; ncu (r02) showed it issue-bound at 200 instructions per vector (64-bit address arithmetic, a
+    // runtime division and five range checks per vector) and, once unrolled, missing the instruction cache.  Hence a FAST
+    // path for whole tiles of 64 / 128 / 256 channels (a thread's channel slot is then fixed, everything per vector is a
+    // few 32-bit operations, the loop over groups of four vectors stays rolled, and the skip vectors of the next group —
+    // across the tile boundary too — are requested before the current group is processed) and a compact generic path for
+    // ragged tiles, other widths and the pooled skip terms.
+    reg_inc<136>();
     const int f = threadIdx.x - 256;
     const int vpr = p.block_n >> 3, nvec = 128 * vpr;
-    const bool single = p.resid_mode == DRB_RES_SAME || p.resid_mode == DRB_RES_FRAME_UP2 || p.resid_mode == DRB_RES_NEAREST_UP_HW;
-    int iter = 0;
-    for (int tile = unit_id; tile < num_tiles; tile += num_units, ++iter) {
-      int t, h0, w0, n0;
-      const bool tile_valid = decode_tile(tile, t, h0, w0, n0);
+    const int rmode = p.resid_mode;
+    const bool single = rmode == DRB_RES_SAME || rmode == DRB_RES_FRAME_UP2 || rmode == DRB_RES_NEAREST_UP_HW;
+    const int rsh = rmode == DRB_RES_NEAREST_UP_HW ? 1 : 0;
+    const int ssh = p.out_scale - 1;                             // out_scale is 1 or 2
+    const int vsh = vpr == 8 ? 3 : (vpr == 16 ? 4 : 5);
+    const int64_t out_frame = static_cast<int64_t>(p.out_H) * p.out_W * p.Cout, res_frame = static_cast<int64_t>(p.rH) * p.rW * p.Cout;
+    const bool fast_shape = (vpr == 8 || vpr == 16 || vpr == 32) && (rmode == DRB_RES_NONE || single) &&
+                            out_frame < (int64_t(1) << 31) && res_frame < (int64_t(1) << 31);
+    const int slot = f & (vpr - 1), row0 = f >> vsh, row_step = 256 >> vsh, ngroups = vpr >> 3;   // fast path only
+    const uint32_t buf_u32 = smem_u32(epi_stage);
+
+    struct TileCtx {
+      int t, h0, w0, n0, oh0, ow0;
+      bool valid, fast;
+      __nv_bfloat16* out_t;            // fast path: output frame + n0 + this thread's channel slot
+      const __nv_bfloat16* res_t;      // fast path: skip-term frame + n0 + slot
+    };
+    auto make_ctx = [&](int tile) {
+      TileCtx c;
+      c.valid = decode_tile(tile, c.t, c.h0, c.w0, c.n0);
+      c.oh0 = c.h0 * p.out_scale + p.out_off_h;
+      c.ow0 = c.w0 * p.out_scale + p.out_off_w;
+      c.fast = fast_shape && c.valid && c.h0 + kTileH <= p.H_out && c.w0 + kTileW <= p.W_out && c.n0 + p.block_n <= p.Cout;
+      c.out_t = p.out + static_cast<int64_t>(c.t) * out_frame + c.n0 + slot * 8;
+      c.res_t = single ? p.resid + static_cast<int64_t>(rmode == DRB_RES_FRAME_UP2 ? (c.t + 1) >> 1 : c.t) * res_frame + c.n0 + slot * 8
+                       : nullptr;
+      return c;
+    };
+    uint4 pf[4] = {};        // skip vectors of the group processed next (fast path, single-source skip terms)
+    auto request_skips = [&](const TileCtx& c, int g) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = row0 + (g * 4 + u) * row_step;
+        const int oh = c.oh0 + ((row >> 4) << ssh), ow = c.ow0 + ((row & 15) << ssh);
+        pf[u] = __ldg(reinterpret_cast<const uint4*>(c.res_t + ((oh >> rsh) * p.rW + (ow >> rsh)) * p.Cout));
+      }
+    };
+
+    int tile = unit_id, iter = 0;
+    TileCtx c{};
+    if (tile < num_tiles) {
+      c = make_ctx(tile);
+      if (c.fast && single) request_skips(c, 0);
+    }
+    for (; tile < num_tiles; ++iter) {
       const int as = iter & 1;
-      const uint8_t* buf = epi_stage + as * kTileBufBytes;
+      const uint32_t buf_a = buf_u32 + as * kTileBufBytes;
+      const int next_tile = tile + num_units;
+      TileCtx nx = c;
       float s1 = 0.f, s2 = 0.f;
-      bool waited = false;
-      for (int k0 = 0; k0 * 256 < nvec; k0 += 4) {
-        int rowv[4], slotv[4];
-        bool okv[4];
-        __nv_bfloat16* outp[4];
-        uint4 skipv[4];
+      mbar_wait(&buf_full[as], (iter >> 1) & 1);
+      if (c.fast) {
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+          uint4 cur[4];
+          uint4 xv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = (k0 + u) * 256 + f;
-          const int row = i / vpr, slot = i - row * vpr;
-          const int h = h0 + row / kTileW, w = w0 + row % kTileW;
-          rowv[u] = row;
-          slotv[u] = slot;
-          okv[u] = tile_valid && i < nvec && h < p.H_out && w < p.W_out && n0 + slot * 8 < p.Cout;
-          const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
-          outp[u] = p.out + ((static_cast<int64_t>(t) * p.out_H + oh) * p.out_W + ow) * p.Cout + n0 + slot * 8;
-          skipv[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (single && okv[u]) {       // the skip rows are requested before the wait for the drained tile
-            int tt = t, hh = oh, ww = ow;
-            if (p.resid_mode == DRB_RES_FRAME_UP2) tt = (t + 1) >> 1;
-            if (p.resid_mode == DRB_RES_NEAREST_UP_HW) { hh >>= 1; ww >>= 1; }
-            skipv[u] = *reinterpret_cast<const uint4*>(p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout + n0 + slot * 8);
+          for (int u = 0; u < 4; ++u) {
+            cur[u] = pf[u];
+            const int row = row0 + (g * 4 + u) * row_step;
+            xv[u] = ld_shared_v4(buf_a + row * 512 + ((slot ^ (row & 31)) << 4));
           }
-        }
-        if (!waited) {
-          mbar_wait(&buf_full[as], (iter >> 1) & 1);
-          waited = true;
-        }
+          if (g + 1 < ngroups) {
+            if (single) request_skips(c, g + 1);
+          } else if (next_tile < num_tiles) {
+            nx = make_ctx(next_tile);
+            if (nx.fast && single) request_skips(nx, 0);
+          }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if ((k0 + u) * 256 + f >= nvec) continue;
-          const uint4 xv = *reinterpret_cast<const uint4*>(buf + rowv[u] * 512 + ((slotv[u] ^ (rowv[u] & 31)) * 16));
-          uint32_t o[4] = {xv.x, xv.y, xv.z, xv.w};
-          if (p.resid_mode != DRB_RES_NONE) {       // uniform
-            float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float rscale = 1.0f;
+          for (int u = 0; u < 4; ++u) {
+            const int row = row0 + (g * 4 + u) * row_step;
+            const int oh = c.oh0 + ((row >> 4) << ssh), ow = c.ow0 + ((row & 15) << ssh);
+            uint32_t o[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
             if (single) {
-              const uint32_t rr[4] = {skipv[u].x, skipv[u].y, skipv[u].z, skipv[u].w};
+              // the drained value is the convolution output already rounded to bf16, as the reference has it before the add
+              const uint32_t rr[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                ra[2 * j] = bf16_lo(rr[j]);
-                ra[2 * j + 1] = bf16_hi(rr[j]);
-              }
-            } else if (okv[u]) {                    // pooled skip terms: 2 or 4 source rows averaged
-              const int row = rowv[u];
-              const int oh = (h0 + row / kTileW) * p.out_scale + p.out_off_h, ow = (w0 + row % kTileW) * p.out_scale + p.out_off_w;
-              const int nsrc = p.resid_mode == DRB_RES_POOL_HW ? 4 : 2;
-              rscale = p.resid_mode == DRB_RES_POOL_HW ? 0.25f : 0.5f;
-              for (int i2 = 0; i2 < nsrc; ++i2) {
-                int tt = t, hh = oh, ww = ow;
-                if (p.resid_mode == DRB_RES_POOL_HW) {
-                  hh = 2 * oh + (i2 >> 1);
-                  ww = 2 * ow + (i2 & 1);
-                  if (hh >= p.rH || ww >= p.rW) continue;
-                } else {
-                  tt = i2 == 0 ? max(2 * t - 1, 0) : 2 * t;
-                }
-                const uint4 rv = *reinterpret_cast<const uint4*>(p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout + n0 + slotv[u] * 8);
-                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  ra[2 * j] += bf16_lo(rr[j]);
-                  ra[2 * j + 1] += bf16_hi(rr[j]);
-                }
-              }
+              for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(bf16_lo(o[j]) + bf16_lo(rr[j]), bf16_hi(o[j]) + bf16_hi(rr[j]));
             }
-            // the drained value is the convolution output already rounded to bf16, as the reference has it before the add
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = pack_bf16x2(bf16_lo(o[j]) + bf16_round(ra[2 * j] * rscale), bf16_hi(o[j]) + bf16_round(ra[2 * j + 1] * rscale));
-          }
-          if (okv[u]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
               s1 += a + b;
               s2 = fmaf(a, a, fmaf(b, b, s2));
             }
-            *reinterpret_cast<uint4*>(outp[u]) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(c.out_t + (oh * p.out_W + ow) * p.Cout) = make_uint4(o[0], o[1], o[2], o[3]);
           }
+        }
+      } else {
+        // generic path: every vector range-checked, 64-bit addresses, 1 / 2 / 4 skip rows averaged
+#pragma unroll 1
+        for (int i = f; i < nvec; i += 256) {
+          const int row = i / vpr, sl = i - row * vpr;
+          const int h = c.h0 + (row >> 4), w = c.w0 + (row & 15);
+          if (!(c.valid && h < p.H_out && w < p.W_out && c.n0 + sl * 8 < p.Cout)) continue;
+          const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
+          const uint4 xv = ld_shared_v4(buf_a + row * 512 + ((sl ^ (row & 31)) << 4));
+          uint32_t o[4] = {xv.x, xv.y, xv.z, xv.w};
+          if (rmode != DRB_RES_NONE) {
+            const int nsrc = single ? 1 : (rmode == DRB_RES_POOL_HW ? 4 : 2);
+            const float rscale = single ? 1.0f : (rmode == DRB_RES_POOL_HW ? 0.25f : 0.5f);
+            float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int i2 = 0; i2 < nsrc; ++i2) {
+              int tt = c.t, hh = oh, ww = ow;
+              if (rmode == DRB_RES_FRAME_UP2) tt = (c.t + 1) >> 1;
+              if (rmode == DRB_RES_NEAREST_UP_HW) { hh >>= 1; ww >>= 1; }
+              if (rmode == DRB_RES_POOL_HW) {
+                hh = 2 * oh + (i2 >> 1);
+                ww = 2 * ow + (i2 & 1);
+                if (hh >= p.rH || ww >= p.rW) continue;
+              } else if (rmode == DRB_RES_POOL_T) {
+                tt = i2 == 0 ? max(2 * c.t - 1, 0) : 2 * c.t;
+              }
+              const uint4 rv = *reinterpret_cast<const uint4*>(p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout + c.n0 + sl * 8);
+              const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ra[2 * j] += bf16_lo(rr[j]);
+                ra[2 * j + 1] += bf16_hi(rr[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = pack_bf16x2(bf16_lo(o[j]) + bf16_round(ra[2 * j] * rscale), bf16_hi(o[j]) + bf16_round(ra[2 * j + 1] * rscale));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
+            s1 += a + b;
+            s2 = fmaf(a, a, fmaf(b, b, s2));
+          }
+          *reinterpret_cast<uint4*>(p.out + ((static_cast<int64_t>(c.t) * p.out_H + oh) * p.out_W + ow) * p.Cout + c.n0 + sl * 8) =
+              make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (next_tile < num_tiles) {
+          nx = make_ctx(next_tile);
+          if (nx.fast && single) request_skips(nx, 0);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&buf_empty[as]);
-      if (p.stats != nullptr && tile_valid) {
+      if (p.stats != nullptr && c.valid) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
           s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
         if (lane == 0) {
-          atomicAdd(&p.stats[2 * t], static_cast<double>(s1));
-          atomicAdd(&p.stats[2 * t + 1], static_cast<double>(s2));
+          atomicAdd(&p.stats[2 * c.t], static_cast<double>(s1));
+          atomicAdd(&p.stats[2 * c.t + 1], static_cast<double>(s2));
         }
       }
+      tile = next_tile;
+      c = nx;
     }
   } else {
     reg_inc<208>();

@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-for k in 1 2; do
-echo "--- old (cvt rounding, runtime modulus)"; DRB200_LIB=/root/repo/lib_old.so python tools/gn_probe.py | head -2
-echo "--- new (ALU rounding, pow2 mask)"; python tools/gn_probe.py | head -2
-done
-echo "--- tokenizer old"; DRB200_LIB=/root/repo/lib_old.so python bench.py --workload tokenizer121 --steps 10 --warmup 3 --no-gpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'])"
-echo "--- tokenizer new"; python bench.py --workload tokenizer121 --steps 10 --warmup 3 --no-gpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'])"
-timeout 300 python -m pytest tests/test_tokenizer_gpu.py -x -q 2>&1 | tail -2
+PROBE_ITERS=1 timeout 800 ncu --set full --clock-control none --import-source on -k regex:conv3d_kernel -c 8 -f -o gpurun_out/conv_split_256_v2 python tools/conv_t_probe.py 256 > gpurun_out/ncu_conv.log 2>&1
+tail -3 gpurun_out/ncu_conv.log
