@@ -43,24 +43,28 @@ constexpr int kABytes = 128 * kBlockK * 2;      // 16 KB
 // (32 KB stages, 6 of them): a third less operand traffic per MMA, which is what lifted the (1,3,3) convolutions from
 // 1370 - 1460 to 1530 - 1590 TFLOP/s (tensor pipe 96.8 % active).
 // kSplit (pair flavour only, chosen for convolutions with few taps): the epilogue is TWO stages on different warps — four
-// "drain" warps move the accumulator (+ bias, rounded to bf16) from tensor memory into one of two 64 KB tile buffers in
-// shared memory, eight "finish" warps stream the buffer out (skip term, GroupNorm sums, fully coalesced 16-byte loads and
-// stores) — because with 1 - 6 k MMA cycles per tile the single-stage epilogue (10 - 13 k cycles of a latency-bound
-// TMEM -> registers -> shared -> global chain on two warps per scheduler) bounded those kernels.  3-stage operand ring
-// (half-tile buffers with a 5-stage ring measured slower on everything but the plain 512-channel (3,1,1) convolution).
+// "drain" warps move the accumulator (+ bias, rounded to bf16) from tensor memory into a ring of four 16 KB buffers in
+// shared memory (one buffer = 128 positions x 64 channels, a quarter of the widest tile), eight "finish" warps stream the
+// buffers out (skip term, GroupNorm sums, fully coalesced 16-byte loads and stores) — because with 1 - 6 k MMA cycles per
+// tile the single-stage epilogue (10 - 13 k cycles of a latency-bound TMEM -> registers -> shared -> global chain on two
+// warps per scheduler) bounded those kernels.  The quarter-tile ring leaves room for a 5-stage operand ring: with the two
+// whole-tile buffers of the first version only 3 stages fitted, and 96 KB of operands in flight per SM cannot cover the
+// L2 latency at the MMA's consumption rate (ncu: the MMA warp waited for operands 37 % of the time, 7 us per tile against
+// 3.6 us of MMA work).
 template <int kCta, bool kSplit>
 struct ConvCfg {
   static constexpr int kBBytes = kMaxN / kCta * kBlockK * 2;   // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;        // 48 KB / 32 KB
-  static constexpr int kStages = kSplit ? 3 : (kCta == 1 ? 4 : 6);
+  static constexpr int kStages = kSplit ? 5 : (kCta == 1 ? 4 : 6);
   static constexpr int kThreads = kSplit ? 512 : 384;
 };
 constexpr int kEpiWarps = 8;                    // single-stage epilogue: two per TMEM lane quadrant, each taking half of the tile's chunks
 constexpr int kEpiStage = kEpiWarps * 4096;     // per epilogue warp: 2 x (32 pixels x 64 B = one 32-channel chunk), XOR-swizzled:
                                                 // [0, 2048) output rows on their way out, [2048, 4096) skip-term rows on their way in
-constexpr int kTileBufBytes = 128 * 512;        // split epilogue: 128 positions x 256 channels bf16, 16-byte slots XOR-swizzled by row
+constexpr int kQuarterBytes = 128 * 128;        // split epilogue: 128 positions x 64 channels bf16, 16-byte slots XOR-swizzled by row
+constexpr int kQuarters = 4;                    // ring of quarter-tile buffers between the drain and the finish warps
 constexpr int kConvSmem = 4 * (kABytes + kMaxN * kBlockK * 2) + 1024 + 256 + kEpiStage;   // the same for all flavours
-static_assert(3 * (kABytes + kMaxN / 2 * kBlockK * 2) + 256 + 2 * kTileBufBytes + 1024 <= kConvSmem, "split flavour must fit");
+static_assert(5 * (kABytes + kMaxN / 2 * kBlockK * 2) + 256 + kQuarters * kQuarterBytes + 1024 <= kConvSmem, "split flavour must fit");
 
 struct ConvMaps {
   CUtensorMap x[4];   // [0] for stride 1; [py*2 + px] parity views for stride 2
@@ -98,10 +102,10 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* buf_full = tmem_empty_bar + 2;     // split epilogue: tile buffer b holds a drained tile / is free again
-  uint64_t* buf_empty = buf_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_empty + 2);
-  uint8_t* epi_stage = smem + kStages * kStageBytes + 256;   // single-stage epilogue staging, or the two tile buffers
+  uint64_t* q_full = tmem_empty_bar + 2;       // split epilogue: quarter buffer b holds drained columns / is free again
+  uint64_t* q_empty = q_full + kQuarters;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + kQuarters);
+  uint8_t* epi_stage = smem + kStages * kStageBytes + 256;   // single-stage epilogue staging, or the quarter-tile ring
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,8 +132,10 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], (kSplit ? 4 : kEpiWarps) * kCta);   // the TMEM-reading warps of every CTA of the group
-      mbar_init(&buf_full[i], 4);                                       // the four drain warps
-      mbar_init(&buf_empty[i], 8);                                      // the eight finish warps
+    }
+    for (int i = 0; i < kQuarters; ++i) {
+      mbar_init(&q_full[i], 4);                                         // the four drain warps
+      mbar_init(&q_empty[i], 8);                                        // the eight finish warps
     }
     fence_barrier_init();
   }
@@ -259,16 +265,17 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     reg_inc<160>();
     const int q = warp_idx & 3;
     const int r = q * 32 + lane;
-    const int nch = (p.block_n + 31) / 32;
+    const int nch = (p.block_n + 31) / 32, nq = (nch + 1) >> 1;
+    const uint32_t ring_u32 = smem_u32(epi_stage);
+    const uint32_t row_off = r * 128, swz = r & 7;
     int iter = 0;
+    uint32_t qc = 0;       // quarters handed over so far: buffer qc % 4, phase (qc / 4) & 1
     for (int tile = unit_id; tile < num_tiles; tile += num_units, ++iter) {
       int t, h0, w0, n0;
       decode_tile(tile, t, h0, w0, n0);
       const int as = iter & 1;
-      mbar_wait(&buf_empty[as], ((iter >> 1) & 1) ^ 1);
       mbar_wait(&tmem_full_bar[as], (iter >> 1) & 1);
       tc_fence_after();
-      uint8_t* row_buf = epi_stage + as * kTileBufBytes + r * 512;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kMaxN;
       uint32_t accbuf[2][32];
       tmem_ld32(taddr, accbuf[0]);
@@ -281,9 +288,21 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           const int cg = n0 + c * 32 + g * 8;
           bias4[g] = cg < p.Cout ? __ldg(reinterpret_cast<const uint4*>(p.bias + cg)) : make_uint4(0u, 0u, 0u, 0u);
         }
+        const uint32_t qi = qc + (c >> 1);
+        if ((c & 1) == 0) mbar_wait(&q_empty[qi & 3], ((qi >> 2) & 1) ^ 1);
         tmem_wait_ld();
         uint32_t (&acc)[32] = accbuf[c & 1];
-        if (c + 1 < nch) tmem_ld32(taddr + (c + 1) * 32, accbuf[(c + 1) & 1]);
+        if (c + 1 < nch) {
+          tmem_ld32(taddr + (c + 1) * 32, accbuf[(c + 1) & 1]);
+        } else {               // the accumulator stage is free as soon as its last columns are in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[as]);
+            else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+          }
+        }
+        const uint32_t dst = ring_u32 + (qi & 3) * kQuarterBytes + row_off;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t bb[4] = {bias4[g].x, bias4[g].y, bias4[g].z, bias4[g].w};
@@ -291,145 +310,124 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             o[j] = pack_bf16x2(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bb[j]), __uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bb[j]));
-          *reinterpret_cast<uint4*>(row_buf + (((c * 4 + g) ^ (r & 31)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+          st_shared_v4(dst + ((((c & 1) * 4 + g) ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+        }
+        if ((c & 1) == 1 || c + 1 == nch) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&q_full[qi & 3]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[as]);
-        else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
-        mbar_arrive(&buf_full[as]);
-      }
+      qc += nq;
     }
   } else if (kSplit) {
     // ------------------------------------------------------------------ split epilogue, stage 2: finish (eight warps, streaming)
-    // Thread f takes the 16-byte vectors f, f + 256, ... of the tile (row-major, block_n / 8 vectors per position): a warp
-    // reads and writes whole channel rows — skip term in, output out — instead of a row per thread.  This stage bounds the
-    // few-tap convolutions; ncu (r02) showed it issue-bound at 200 instructions per vector (64-bit address arithmetic, a
-    // runtime division and five range checks per vector) and, once unrolled, missing the instruction cache.  Hence a FAST
-    // path for whole tiles of 64 / 128 / 256 channels (a thread's channel slot is then fixed, everything per vector is a
-    // few 32-bit operations, the loop over groups of four vectors stays rolled, and the skip vectors of the next group —
-    // across the tile boundary too — are requested before the current group is processed) and a compact generic path for
-    // ragged tiles, other widths and the pooled skip terms.
+    // Per quarter buffer (128 positions x 64 channels) thread f takes the 16-byte channel slot f % 8 of the positions
+    // f / 8 + 32 u, u = 0..3: a warp reads and writes whole 128-byte lines — skip term in, output out.  The positions are
+    // the same for every quarter of a tile, so everything per vector is one 32-bit add on offsets computed once per tile.
+    // This stage bounded the few-tap convolutions; ncu (r02) showed its first version issue-bound at 200 instructions per
+    // vector (64-bit address arithmetic, a runtime division and five range checks per vector) and, once unrolled, missing
+    // the instruction cache.  The skip vectors of the NEXT quarter — across the tile boundary too — are requested before
+    // the current one is processed.
     reg_inc<136>();
     const int f = threadIdx.x - 256;
-    const int vpr = p.block_n >> 3, nvec = 128 * vpr;
+    const int slot = f & 7, prow = f >> 3;                        // rows prow + 32 u: (row & 7) is the same for all four
+    const int nq = (p.block_n + 63) >> 6;
     const int rmode = p.resid_mode;
     const bool single = rmode == DRB_RES_SAME || rmode == DRB_RES_FRAME_UP2 || rmode == DRB_RES_NEAREST_UP_HW;
     const int rsh = rmode == DRB_RES_NEAREST_UP_HW ? 1 : 0;
-    const int ssh = p.out_scale - 1;                             // out_scale is 1 or 2
-    const int vsh = vpr == 8 ? 3 : (vpr == 16 ? 4 : 5);
+    const int ssh = p.out_scale - 1;                              // out_scale is 1 or 2
     const int64_t out_frame = static_cast<int64_t>(p.out_H) * p.out_W * p.Cout, res_frame = static_cast<int64_t>(p.rH) * p.rW * p.Cout;
-    const bool fast_shape = (vpr == 8 || vpr == 16 || vpr == 32) && (rmode == DRB_RES_NONE || single) &&
-                            out_frame < (int64_t(1) << 31) && res_frame < (int64_t(1) << 31);
-    const int slot = f & (vpr - 1), row0 = f >> vsh, row_step = 256 >> vsh, ngroups = vpr >> 3;   // fast path only
-    const uint32_t buf_u32 = smem_u32(epi_stage);
+    const uint32_t my_u32 = smem_u32(epi_stage) + prow * 128 + ((slot ^ (prow & 7)) << 4);
 
     struct TileCtx {
-      int t, h0, w0, n0, oh0, ow0;
-      bool valid, fast;
-      __nv_bfloat16* out_t;            // fast path: output frame + n0 + this thread's channel slot
-      const __nv_bfloat16* res_t;      // fast path: skip-term frame + n0 + slot
+      int t, h0, w0, n0;
+      bool valid;
+      int rel_o[4];                    // element offset of position u in its output frame, -1: nothing to store
+      int rel_r[4];                    // the same in the skip-term frame (single-source skip terms)
+      __nv_bfloat16* out_t;            // output frame + n0 + this thread's channel slot
+      const __nv_bfloat16* res_t;      // skip-term frame + n0 + slot
     };
     auto make_ctx = [&](int tile) {
       TileCtx c;
       c.valid = decode_tile(tile, c.t, c.h0, c.w0, c.n0);
-      c.oh0 = c.h0 * p.out_scale + p.out_off_h;
-      c.ow0 = c.w0 * p.out_scale + p.out_off_w;
-      c.fast = fast_shape && c.valid && c.h0 + kTileH <= p.H_out && c.w0 + kTileW <= p.W_out && c.n0 + p.block_n <= p.Cout;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = prow + 32 * u;
+        const int h = c.h0 + (row >> 4), w = c.w0 + (row & 15);
+        const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
+        c.rel_o[u] = (c.valid && h < p.H_out && w < p.W_out) ? (oh * p.out_W + ow) * p.Cout : -1;
+        c.rel_r[u] = ((oh >> rsh) * p.rW + (ow >> rsh)) * p.Cout;
+      }
       c.out_t = p.out + static_cast<int64_t>(c.t) * out_frame + c.n0 + slot * 8;
       c.res_t = single ? p.resid + static_cast<int64_t>(rmode == DRB_RES_FRAME_UP2 ? (c.t + 1) >> 1 : c.t) * res_frame + c.n0 + slot * 8
                        : nullptr;
       return c;
     };
-    uint4 pf[4] = {};        // skip vectors of the group processed next (fast path, single-source skip terms)
-    auto request_skips = [&](const TileCtx& c, int g) {
+    // channels [ch, ch + 8) of quarter qq exist in this n-tile
+    auto col_ok = [&](const TileCtx& c, int qq) { const int ch = qq * 64 + slot * 8; return ch < p.block_n && c.n0 + ch < p.Cout; };
+    uint4 pf[4] = {};        // skip vectors of the quarter processed next
+    auto request_skips = [&](const TileCtx& c, int qq) {
+      const bool cok = col_ok(c, qq);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int row = row0 + (g * 4 + u) * row_step;
-        const int oh = c.oh0 + ((row >> 4) << ssh), ow = c.ow0 + ((row & 15) << ssh);
-        pf[u] = __ldg(reinterpret_cast<const uint4*>(c.res_t + ((oh >> rsh) * p.rW + (ow >> rsh)) * p.Cout));
-      }
+      for (int u = 0; u < 4; ++u)
+        pf[u] = (cok && c.rel_o[u] >= 0) ? __ldg(reinterpret_cast<const uint4*>(c.res_t + c.rel_r[u] + qq * 64)) : make_uint4(0u, 0u, 0u, 0u);
     };
 
-    int tile = unit_id, iter = 0;
+    int tile = unit_id;
+    uint32_t qc = 0;
     TileCtx c{};
     if (tile < num_tiles) {
       c = make_ctx(tile);
-      if (c.fast && single) request_skips(c, 0);
+      if (single) request_skips(c, 0);
     }
-    for (; tile < num_tiles; ++iter) {
-      const int as = iter & 1;
-      const uint32_t buf_a = buf_u32 + as * kTileBufBytes;
+    while (tile < num_tiles) {
       const int next_tile = tile + num_units;
       TileCtx nx = c;
       float s1 = 0.f, s2 = 0.f;
-      mbar_wait(&buf_full[as], (iter >> 1) & 1);
-      if (c.fast) {
 #pragma unroll 1
-        for (int g = 0; g < ngroups; ++g) {
-          uint4 cur[4];
-          uint4 xv[4];
+      for (int qq = 0; qq < nq; ++qq, ++qc) {
+        const uint32_t src = my_u32 + (qc & 3) * kQuarterBytes;
+        uint4 cur[4], xv[4];
+        mbar_wait(&q_full[qc & 3], (qc >> 2) & 1);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            cur[u] = pf[u];
-            const int row = row0 + (g * 4 + u) * row_step;
-            xv[u] = ld_shared_v4(buf_a + row * 512 + ((slot ^ (row & 31)) << 4));
-          }
-          if (g + 1 < ngroups) {
-            if (single) request_skips(c, g + 1);
-          } else if (next_tile < num_tiles) {
-            nx = make_ctx(next_tile);
-            if (nx.fast && single) request_skips(nx, 0);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int row = row0 + (g * 4 + u) * row_step;
-            const int oh = c.oh0 + ((row >> 4) << ssh), ow = c.ow0 + ((row & 15) << ssh);
-            uint32_t o[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-            if (single) {
-              // the drained value is the convolution output already rounded to bf16, as the reference has it before the add
-              const uint32_t rr[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(bf16_lo(o[j]) + bf16_lo(rr[j]), bf16_hi(o[j]) + bf16_hi(rr[j]));
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
-              s1 += a + b;
-              s2 = fmaf(a, a, fmaf(b, b, s2));
-            }
-            *reinterpret_cast<uint4*>(c.out_t + (oh * p.out_W + ow) * p.Cout) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
+        for (int u = 0; u < 4; ++u) {
+          cur[u] = pf[u];
+          xv[u] = ld_shared_v4(src + u * 4096);
         }
-      } else {
-        // generic path: every vector range-checked, 64-bit addresses, 1 / 2 / 4 skip rows averaged
-#pragma unroll 1
-        for (int i = f; i < nvec; i += 256) {
-          const int row = i / vpr, sl = i - row * vpr;
-          const int h = c.h0 + (row >> 4), w = c.w0 + (row & 15);
-          if (!(c.valid && h < p.H_out && w < p.W_out && c.n0 + sl * 8 < p.Cout)) continue;
-          const int oh = h * p.out_scale + p.out_off_h, ow = w * p.out_scale + p.out_off_w;
-          const uint4 xv = ld_shared_v4(buf_a + row * 512 + ((sl ^ (row & 31)) << 4));
-          uint32_t o[4] = {xv.x, xv.y, xv.z, xv.w};
-          if (rmode != DRB_RES_NONE) {
-            const int nsrc = single ? 1 : (rmode == DRB_RES_POOL_HW ? 4 : 2);
-            const float rscale = single ? 1.0f : (rmode == DRB_RES_POOL_HW ? 0.25f : 0.5f);
+        if (qq + 1 < nq) {
+          if (single) request_skips(c, qq + 1);
+        } else if (next_tile < num_tiles) {
+          nx = make_ctx(next_tile);
+          if (single) request_skips(nx, 0);
+        }
+        const bool cok = col_ok(c, qq);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!cok || c.rel_o[u] < 0) continue;
+          uint32_t o[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+          if (single) {
+            // the drained value is the convolution output already rounded to bf16, as the reference has it before the add
+            const uint32_t rr[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(bf16_lo(o[j]) + bf16_lo(rr[j]), bf16_hi(o[j]) + bf16_hi(rr[j]));
+          } else if (rmode != DRB_RES_NONE) {       // pooled skip terms (two resampling convolutions per net): 2 or 4 rows averaged
+            const int row = prow + 32 * u;
+            const int oh = (c.h0 + (row >> 4)) * p.out_scale + p.out_off_h, ow = (c.w0 + (row & 15)) * p.out_scale + p.out_off_w;
+            const int nsrc = rmode == DRB_RES_POOL_HW ? 4 : 2;
+            const float rscale = rmode == DRB_RES_POOL_HW ? 0.25f : 0.5f;
             float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int i2 = 0; i2 < nsrc; ++i2) {
               int tt = c.t, hh = oh, ww = ow;
-              if (rmode == DRB_RES_FRAME_UP2) tt = (c.t + 1) >> 1;
-              if (rmode == DRB_RES_NEAREST_UP_HW) { hh >>= 1; ww >>= 1; }
               if (rmode == DRB_RES_POOL_HW) {
                 hh = 2 * oh + (i2 >> 1);
                 ww = 2 * ow + (i2 & 1);
                 if (hh >= p.rH || ww >= p.rW) continue;
-              } else if (rmode == DRB_RES_POOL_T) {
+              } else {
                 tt = i2 == 0 ? max(2 * c.t - 1, 0) : 2 * c.t;
               }
-              const uint4 rv = *reinterpret_cast<const uint4*>(p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout + c.n0 + sl * 8);
+              const uint4 rv = *reinterpret_cast<const uint4*>(p.resid + ((static_cast<int64_t>(tt) * p.rH + hh) * p.rW + ww) * p.Cout +
+                                                               c.n0 + qq * 64 + slot * 8);
               const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -447,16 +445,11 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             s1 += a + b;
             s2 = fmaf(a, a, fmaf(b, b, s2));
           }
-          *reinterpret_cast<uint4*>(p.out + ((static_cast<int64_t>(c.t) * p.out_H + oh) * p.out_W + ow) * p.Cout + c.n0 + sl * 8) =
-              make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(c.out_t + c.rel_o[u] + qq * 64) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        if (next_tile < num_tiles) {
-          nx = make_ctx(next_tile);
-          if (nx.fast && single) request_skips(nx, 0);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_empty[qc & 3]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&buf_empty[as]);
       if (p.stats != nullptr && c.valid) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -791,13 +784,19 @@ extern "C" int drb_conv3d_cl(const drb_conv3d_args* a, void* stream) {
   p.stats = a->stats;
   const int units = ((tiles_m + cta - 1) / cta) * tiles_n;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // The split, two-stage epilogue pays where the single-stage one bounds the kernel: up to 12 k-blocks per tile (1x1x1,
-  // 3x1x1 at <= 256 channels), or up to 24 when a skip term doubles the epilogue's memory work (tools/conv_t_probe.py:
-  // (3,1,1) 256 -> 256 with skip 0.57 -> 0.44 ms, 512 -> 512 with skip 0.187 -> 0.162; plain 512 -> 512 is better off with
-  // the deeper operand ring of the single-stage flavour, 0.130 vs 0.144).
+  // The split, two-stage epilogue pays where the single-stage one bounds the kernel: up to 36 k-blocks per tile (1x1x1,
+  // 3x1x1, the 2x2 sub-pixel convolutions, 3x3 at <= 256 channels: tools/conv_t_probe.py, tools/vae_kernel_probe.py, r02 —
+  // (3,1,1) 256 -> 256 with skip 0.57 -> 0.35 ms, 512 -> 512 with skip 0.187 -> 0.147, (1,2,2) 512 -> 512 0.37 -> 0.32,
+  // (1,3,3) 256 -> 256 -4 %; at 72 k-blocks the deeper operand ring of the single-stage flavour wins).  Pooled skip terms
+  // (2 or 4 source rows per output vector) are slow in the streaming finish stage: those only up to 12 k-blocks.
   static const int split_ok = [] { const char* e = getenv("DRB_CONV_SPLIT"); return e ? atoi(e) : 1; }();   // 0: A/B measurements
+  static const int split_kb = [] { const char* e = getenv("DRB_CONV_SPLIT_KB"); return e ? atoi(e) : 36; }();
   const int num_kb = taps * (a->Cin / kBlockK);
-  const bool split = cta == 2 && split_ok && (num_kb <= 12 || (num_kb <= 24 && a->resid != nullptr));
+  const bool pooled = a->resid_mode == DRB_RES_POOL_HW || a->resid_mode == DRB_RES_POOL_T;
+  // the finish stage addresses inside one frame with 32-bit element offsets
+  const bool frames_fit = static_cast<int64_t>(p.out_H) * p.out_W * p.Cout < (int64_t(1) << 31) &&
+                          static_cast<int64_t>(p.rH) * p.rW * p.Cout < (int64_t(1) << 31);
+  const bool split = cta == 2 && split_ok && frames_fit && num_kb <= (pooled ? (split_kb < 12 ? split_kb : 12) : split_kb);
   if (split) return launch_conv<2, true>(maps, p, units, s);
   return cta == 2 ? launch_conv<2, false>(maps, p, units, s) : launch_conv<1, false>(maps, p, units, s);
 }

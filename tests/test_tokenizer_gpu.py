@@ -72,17 +72,31 @@ def test_conv3d_matches_torch(shape, k, pad):
     assert torch.allclose(stats, stats_of(got).double(), rtol=1e-3, atol=1e-2)
 
 
-def test_conv3d_skip_term_and_stats():
+@pytest.mark.parametrize("T,H,W,c,k", [
+    (3, 16, 16, 128, (3, 1, 1)),     # whole tiles, two quarter buffers per tile
+    (2, 9, 21, 96, (3, 1, 1)),       # ragged tiles, a half-filled quarter buffer
+    (2, 10, 12, 384, (1, 1, 1)),     # second n-tile only half inside Cout
+    (3, 8, 16, 192, (1, 3, 3)),      # three quarter buffers per tile: the buffer ring wraps inside a tile
+    (5, 24, 32, 256, (3, 1, 1)),     # more tiles than CTAs hold at once: skip vectors requested across the tile boundary
+    (2, 16, 16, 512, (1, 3, 3)),     # 72 k-blocks: the single-stage epilogue
+])
+def test_conv3d_skip_term_and_stats(T, H, W, c, k):
+    """skip term + GroupNorm sums through both epilogue flavours (the split one up to 36 k-blocks per tile)"""
     from drb200 import ops
-    T, H, W, c = 3, 16, 16, 128
-    w, b = rand_conv(c, c, 3, 1, 1, seed=3)
-    x = torch.randn(1, c, T, H, W, device=DEV, generator=gen(4)).bfloat16()
+    cin = c if c % 64 == 0 else 64               # Cin comes in 64-channel chunks; Cout in multiples of 16
+    w, b = rand_conv(c, cin, *k, seed=3)
+    pad = 1 if k[1] == 3 else 0
+    x = torch.randn(1, cin, T, H, W, device=DEV, generator=gen(4)).bfloat16()
     skip = torch.randn(1, c, T, H, W, device=DEV, generator=gen(5)).bfloat16()
     stats = torch.zeros(T, 2, device=DEV, dtype=torch.float64)
-    got = ops.conv3d_cl(cl(x), wcl(w), b, resid=cl(skip), resid_mode=1, stats=stats)
-    ref = cl(vo.causal_conv3d(sd32(w, b), "c", x.float()) + skip.float())
+    got = ops.conv3d_cl(cl(x), wcl(w), b, pad_h=pad, pad_w=pad, resid=cl(skip), resid_mode=1, stats=stats)
+    conv = cl(vo.causal_conv3d(sd32(w, b), "c", x.float(), padding=pad))
+    ref = conv.bfloat16().float() + cl(skip).float()      # the reference rounds the convolution output before the add
     assert rel_l2(got, ref) <= 4e-3
     assert torch.allclose(stats, stats_of(got).double(), rtol=1e-3, atol=1e-2)
+    # the same convolution without the skip term, then added in torch: bit-identical (one rounding each, same order)
+    plain = ops.conv3d_cl(cl(x), wcl(w), b, pad_h=pad, pad_w=pad)
+    assert torch.equal(got, (plain.float() + cl(skip).float()).bfloat16())
 
 
 @pytest.mark.parametrize("T,H,W", [(7, 16, 32), (1, 8, 8), (5, 12, 20)])
