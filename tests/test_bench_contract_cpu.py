@@ -33,3 +33,21 @@ def test_b200_arm_refuses_to_run_without_a_gpu():
                        text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
     assert r.stdout.strip() == ""
+
+
+def test_attention_traffic_record_belongs_to_the_committed_kernel_source():
+    """`roofline.traffic` is only reported while csrc/attention.cu is the file ncu profiled: the record in profiles/ carries
+    the sha256 of that source, and a stale record (kernel edited, capture not repeated) must be caught here, not at round end."""
+    import hashlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "attention_traffic.json")) as f:
+        rec = json.load(f)
+    with open(os.path.join(root, "diffusionrenderer-comfyui_b200", "csrc", "attention.cu"), "rb") as f:
+        sha = hashlib.sha256(f.read()).hexdigest()
+    assert rec["attention_cu_sha256"] == sha, "attention.cu changed: repeat the ncu --set full capture (tools/attn_ab.py 28160 32 2)"
+    sys.path.insert(0, root)
+    import bench
+    val, src, stale = bench.attention_traffic(28160, 32)
+    assert not stale and val == rec["traffic_bytes"]["28160x32"] and os.path.exists(os.path.join(root, src.split(" ")[0]))
+    # traffic within 5 % of the algorithmic bytes (Q, K, V read once, O written once): no wasted re-reads
+    assert abs(val / rec["algorithmic_bytes"] - 1.0) < 0.05
