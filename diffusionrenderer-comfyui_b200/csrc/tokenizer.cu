@@ -233,8 +233,9 @@ frame_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ sta
   }
 }
 
-// round-to-nearest-even to bf16 precision with integer ALU ops (finite inputs): the conversion instruction shares the XU pipe
-// with the exponential and the reciprocal of SiLU, which ncu shows 79 % busy in this kernel
+// round-to-nearest-even to bf16 precision with integer ALU ops, FINITE inputs only: the conversion instruction shares the
+// XU pipe with the exponential and the reciprocal of SiLU, which ncu shows 79 % busy in this kernel.  (The GPU's canonical
+// NaN, 0x7fffffff, would be carried into -0 by the rounding add: the caller re-injects non-finite inputs, see below.)
 __device__ __forceinline__ float bf16_round_alu(float x) {
   uint32_t u = __float_as_uint(x);
   u += 0x7fffu + ((u >> 16) & 1u);
@@ -272,13 +273,15 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float y0 = bf16_round_alu((bf16_lo(vw[j]) - mean) * rstd * bf16_lo(gw[j]) + bf16_lo(bw[j]));
-      float y1 = bf16_round_alu((bf16_hi(vw[j]) - mean) * rstd * bf16_hi(gw[j]) + bf16_hi(bw[j]));
+      float y0 = (bf16_lo(vw[j]) - mean) * rstd * bf16_lo(gw[j]) + bf16_lo(bw[j]);
+      float y1 = (bf16_hi(vw[j]) - mean) * rstd * bf16_hi(gw[j]) + bf16_hi(bw[j]);
       if (silu) {   // x * sigmoid(x): exp and reciprocal are both MUFU ops (the kernel's floor); no full-precision division
-        y0 = __fdividef(y0, 1.0f + __expf(-y0));
-        y1 = __fdividef(y1, 1.0f + __expf(-y1));
+        const float r0 = bf16_round_alu(y0), r1 = bf16_round_alu(y1);      // the reference rounds between the norm and SiLU
+        // + 0 * y: nothing for finite y (the zero carries y's sign), NaN for a NaN / Inf y, which the integer rounding lost
+        y0 = fmaf(y0, 0.0f, __fdividef(r0, 1.0f + __expf(-r0)));
+        y1 = fmaf(y1, 0.0f, __fdividef(r1, 1.0f + __expf(-r1)));
       }
-      o[j] = pack_bf16x2(y0, y1);
+      o[j] = pack_bf16x2(y0, y1);   // the conversion rounds (once, for the identity activation) and keeps NaN / Inf
     }
     dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }

@@ -182,6 +182,21 @@ def test_groupnorm_apply_and_frame_stats(silu):
     assert (got == ref).float().mean() > 0.97      # incl. torch's bf16-rounded mean / rstd (see tokenizer.cu)
 
 
+def test_groupnorm_apply_propagates_nan_and_inf():
+    """the integer round-to-nearest-even of the normalised value must not carry a NaN (0x7fffffff on the GPU) into -0"""
+    from drb200 import ops
+    T, H, W, c = 1, 8, 8, 64
+    x = torch.randn(T, H, W, c, device=DEV, generator=gen(31)).bfloat16()
+    stats = ops.frame_stats(x)
+    x[0, 1, 2, 3] = float("nan")
+    x[0, 4, 5, 6] = float("inf")
+    ones, zeros = torch.ones(c, device=DEV, dtype=torch.bfloat16), torch.zeros(c, device=DEV, dtype=torch.bfloat16)
+    for silu in (False, True):
+        got = ops.groupnorm_apply(x, stats, ones, zeros, silu)
+        assert torch.isnan(got[0, 1, 2, 3]) and not torch.isfinite(got[0, 4, 5, 6])    # SiLU(+Inf) may come out as NaN
+        assert torch.isfinite(got.float()).sum() == got.numel() - 2
+
+
 def test_softmax_transpose_temporal_attention():
     from drb200 import ops
     n, cols, ld = 70, 77, 80
