@@ -38,3 +38,14 @@ def test_bench_only_touches_the_oracle_in_the_cpu_reference_leg():
     top = [m for node in tree.body for m in ([a.name for a in node.names] if isinstance(node, ast.Import) else
                                              [node.module or ""] if isinstance(node, ast.ImportFrom) else [])]
     assert not any(m.split(".")[0] == "oracle" for m in top)
+
+
+def test_integration_guide_names_every_declared_entry_point():
+    """INTEGRATION.md is the maintainer's map from reference call sites to the C ABI: no declared symbol may be missing"""
+    import re
+    with open(os.path.join(ROOT, "include", "drb200.h")) as f:
+        declared = set(re.findall(r"\b(drb_[a-z0-9_]+)\s*\(", f.read()))
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        guide = f.read()
+    missing = sorted(s for s in declared if s not in guide)
+    assert len(declared) >= 48 and not missing, missing
