@@ -89,7 +89,12 @@ def test_conv3d_skip_term_and_stats(T, H, W, c, k):
     x = torch.randn(1, cin, T, H, W, device=DEV, generator=gen(4)).bfloat16()
     skip = torch.randn(1, c, T, H, W, device=DEV, generator=gen(5)).bfloat16()
     stats = torch.zeros(T, 2, device=DEV, dtype=torch.float64)
-    got = ops.conv3d_cl(cl(x), wcl(w), b, pad_h=pad, pad_w=pad, resid=cl(skip), resid_mode=1, stats=stats)
+    # the output sits between two guard regions: a store outside [T, H, W, c] (ragged tiles, half-filled buffers) would show
+    n_out, guard = T * H * W * c, 4096
+    buf = torch.full((n_out + 2 * guard,), 777.0, device=DEV, dtype=torch.bfloat16)
+    got = ops.conv3d_cl(cl(x), wcl(w), b, pad_h=pad, pad_w=pad, resid=cl(skip), resid_mode=1, stats=stats,
+                        out=buf[guard:guard + n_out].view(T, H, W, c))
+    assert (buf[:guard] == 777.0).all() and (buf[guard + n_out:] == 777.0).all()
     conv = cl(vo.causal_conv3d(sd32(w, b), "c", x.float(), padding=pad))
     ref = conv.bfloat16().float() + cl(skip).float()      # the reference rounds the convolution output before the add
     assert rel_l2(got, ref) <= 4e-3
