@@ -219,8 +219,12 @@ def run_reference(args, wl):
     # `value` is the extrapolated whole-forward rate the sample implies, in the B200 arm's unit
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * t_sample, "ms_per_full_step_extrapolated": 1000.0 / value,
-            "extrapolated": True, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": config_block(args, wl, 1),
+            "extrapolated": True, "higher_is_better": True,
+            # the same job as the B200 arm at this N (one video, total work fixed, when that arm runs context-parallel)
+            "scaling": "strong" if args.gpus > 1 and args.parallel in ("auto", "cp", "ring") else "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": dict(config_block(args, wl, 1), parallelism="reference algorithm on the host cores of rank 0 (no GPU); the B200 arm "
+                                                                  f"at --gpus {args.gpus} runs the same workload on {args.gpus} GPU(s)"),
             "cpu_baseline": dict(info, value=value, unit=UNIT),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
