@@ -181,7 +181,13 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
   reg_dec<kSplit ? 56 : 72>();
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The WHOLE warp runs the loop in uniform control flow and one elected lane issues (as the MMA warp does): box
+    // coordinates, barrier and shared-memory addresses then live in uniform registers, which is what UTMALDG reads.  A
+    // lane-divergent producer paid an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence per operand — about 60 single-lane
+    // instructions per k-block, which on a scheduler shared with busy drain and finish warps took 880 cycles against the
+    // 512 the k-block's MMAs need (ncu, split flavour: the producer warp was issuing in 80 % of its samples).
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       const int b_rows = p.block_n / kCta;                               // W rows this CTA stages
@@ -206,16 +212,19 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           for (int cc = 0; cc < cchunks; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kStageBytes;
-            if constexpr (kCta == 1) {
-              mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-              tma_load_4d(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
-              tma_load_2d(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK, n0);
-            } else {   // both CTAs' bytes are accounted on the leader's barrier
-              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx * 2);
-              tma_load_4d_pair(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
-              tma_load_2d_pair(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK,
-                               n0 + static_cast<int>(cta_rank) * b_rows);
+            if (issuer) {
+              if constexpr (kCta == 1) {
+                mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                tma_load_4d(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
+                tma_load_2d(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK, n0);
+              } else {   // both CTAs' bytes are accounted on the leader's barrier
+                if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx * 2);
+                tma_load_4d_pair(sa, &maps.x[mi], &full_bar[stage], cc * kBlockK, wsrc, hs, ts);
+                tma_load_2d_pair(sa + kABytes, &maps.w, &full_bar[stage], tap * p.Cin + cc * kBlockK,
+                                 n0 + static_cast<int>(cta_rank) * b_rows);
+              }
             }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
