@@ -392,7 +392,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
     while (tile < num_tiles) {
       const int next_tile = tile + num_units;
       TileCtx nx = c;
-      float s1 = 0.f, s2 = 0.f;
+      uint64_t s1p = f32x2_pack(0.f, 0.f), s2p = s1p;    // GroupNorm sums of the even / odd channels (packed fp32x2 lanes)
 #pragma unroll 1
       for (int qq = 0; qq < nq; ++qq, ++qc) {
         const uint32_t src = my_u32 + (qc & 3) * kQuarterBytes;
@@ -418,7 +418,8 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
             // the drained value is the convolution output already rounded to bf16, as the reference has it before the add
             const uint32_t rr[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(bf16_lo(o[j]) + bf16_lo(rr[j]), bf16_hi(o[j]) + bf16_hi(rr[j]));
+            for (int j = 0; j < 4; ++j) o[j] = bf16x2_add(o[j], rr[j]);   // == bf16(fp32(a) + fp32(b)): the fp32 sum of two bf16 is
+                                                                          // exact or rounds to the larger operand, a bf16 already
           } else if (rmode != DRB_RES_NONE) {       // pooled skip terms (two resampling convolutions per net): 2 or 4 rows averaged
             const int row = prow + 32 * u;
             const int oh = (c.h0 + (row >> 4)) * p.out_scale + p.out_off_h, ow = (c.w0 + (row & 15)) * p.out_scale + p.out_off_w;
@@ -450,9 +451,9 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
-            s1 += a + b;
-            s2 = fmaf(a, a, fmaf(b, b, s2));
+            const uint64_t ab = f32x2_pack(bf16_lo(o[j]), bf16_hi(o[j]));
+            s1p = f32x2_add(s1p, ab);
+            s2p = f32x2_fma(ab, ab, s2p);
           }
           *reinterpret_cast<uint4*>(c.out_t + c.rel_o[u] + qq * 64) = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -460,6 +461,11 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p) {
         if (lane == 0) mbar_arrive(&q_empty[qc & 3]);
       }
       if (p.stats != nullptr && c.valid) {
+        float s1, s2, s1b, s2b;
+        f32x2_unpack(s1p, s1, s1b);
+        f32x2_unpack(s2p, s2, s2b);
+        s1 += s1b;
+        s2 += s2b;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
