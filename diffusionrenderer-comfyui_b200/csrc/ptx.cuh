@@ -113,11 +113,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the thread may stay suspended up to that long before the instruction returns
+// false; it is woken as soon as the phase completes either way.  Without the hint a waiting warp came back every ~100
+// cycles and spent a tenth of its scheduler's issue slots on the retry loop (ncu, convolution drain / finish warps).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+#ifndef DRB_MBAR_HINT_NS
+#define DRB_MBAR_HINT_NS 2000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, DRB_MBAR_HINT_NS)) {
     if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > DRB_WATCHDOG_NS) {
 #ifdef DRB_WATCHDOG_PRINTF
       printf("drb200 watchdog: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n",
